@@ -1,0 +1,483 @@
+// Host side of K1: weight / bias packing kernels and the C-ABI entry points that drive the
+// layer engine (sdrm_create, sdrm_denoiser_pack, sdrm_decoder_pack, sdrm_sample, sdrm_probe_linear).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/sdrm_b200.h"
+#include "host_util.h"
+#include "layer_engine.cuh"
+#include "ptx_sm100.cuh"
+
+namespace sdrm {
+
+__global__ void sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P);
+
+// ------------------------------------------------------------------------------------------------
+// geometry of one dense layer on the engine
+// ------------------------------------------------------------------------------------------------
+struct Geom {
+  int N = 0, K = 0, NCH = 0, NC = 0, Np = 0, KB = 0, kmma_last = 0;
+  size_t img_bytes() const { return static_cast<size_t>(NCH) * KB * NC * 128; }  // one image (hi or lo)
+};
+static Geom make_geom(int N, int K) {
+  Geom g;
+  g.N = N; g.K = K;
+  g.NCH = (N + MAX_NC - 1) / MAX_NC;
+  const int per = (N + g.NCH - 1) / g.NCH;
+  g.NC = ((per + 15) / 16) * 16;
+  g.Np = g.NCH * g.NC;
+  g.KB = (K + KBLK - 1) / KBLK;
+  const int rem = K - KBLK * (g.KB - 1);
+  g.kmma_last = (rem + 15) / 16;
+  return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing kernels
+// ------------------------------------------------------------------------------------------------
+// W fp32 [N, ldw] (columns col_off .. col_off+K) -> bf16 hi (and lo) tile images
+__global__ void pack_weight_kernel(const float* __restrict__ W, int N, int K, long long ldw, int col_off,
+                                   uint8_t* __restrict__ img_hi, uint8_t* __restrict__ img_lo, int NCH, int NC, int KB) {
+  const long long total = static_cast<long long>(NCH) * KB * NC * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx & 7);
+    long long t = idx >> 3;
+    const int r = static_cast<int>(t % NC); t /= NC;
+    const int kb = static_cast<int>(t % KB);
+    const int c = static_cast<int>(t / KB);
+    const int n = c * NC + r;
+    const int k0 = kb * KBLK + j * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = 0.f, v1 = 0.f;
+      if (n < N) {
+        if (k0 + 2 * e < K) v0 = W[n * ldw + col_off + k0 + 2 * e];
+        if (k0 + 2 * e + 1 < K) v1 = W[n * ldw + col_off + k0 + 2 * e + 1];
+      }
+      const float h0 = bf16_round(v0), h1 = bf16_round(v1);
+      hi[e] = pack_bf16x2(h0, h1);
+      lo[e] = pack_bf16x2(v0 - h0, v1 - h1);
+    }
+    const size_t off = ((static_cast<size_t>(c) * KB + kb) * NC + r) * 128 + ((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(img_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (img_lo) *reinterpret_cast<uint4*>(img_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+// A fp32 [M, K] -> per-tile activation images (hi / lo) for the probe entry
+__global__ void pack_act_kernel(const float* __restrict__ A, long long M, int K, uint8_t* __restrict__ scratch,
+                                size_t scratch_stride, size_t act_buf_bytes, int KB) {
+  const long long n_tiles = (M + TILE_M - 1) / TILE_M;
+  const long long total = n_tiles * KB * TILE_M * 8;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = static_cast<int>(idx & 7);
+    long long t = idx >> 3;
+    const int r = static_cast<int>(t % TILE_M); t /= TILE_M;
+    const int kb = static_cast<int>(t % KB);
+    const long long tile = t / KB;
+    const long long row = tile * TILE_M + r;
+    const int k0 = kb * KBLK + j * 8;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = 0.f, v1 = 0.f;
+      if (row < M) {
+        if (k0 + 2 * e < K) v0 = A[row * K + k0 + 2 * e];
+        if (k0 + 2 * e + 1 < K) v1 = A[row * K + k0 + 2 * e + 1];
+      }
+      const float h0 = bf16_round(v0), h1 = bf16_round(v1);
+      hi[e] = pack_bf16x2(h0, h1);
+      lo[e] = pack_bf16x2(v0 - h0, v1 - h1);
+    }
+    uint8_t* base = scratch + static_cast<size_t>(tile) * scratch_stride;
+    const size_t off = static_cast<size_t>(kb) * A_TILE_BYTES + r * 128 + ((j ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + act_buf_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+__global__ void pad_bias_kernel(const float* __restrict__ b, int N, float* __restrict__ out, int Np) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x)
+    out[i] = (b != nullptr && i < N) ? b[i] : 0.0f;
+}
+
+// Hoisted timestep embedding (SDRM.timestep_embedding + emb_layer + the emb columns of dnn.0,
+// train_SDRM.py:98-112): bias0[i][n] = b0[n] + sum_t W0[n][L+t] * (be[t] + sum_s We[t][s] temb_i[s]).
+// One block per step i in [0, T].
+__global__ void bias_table_kernel(const float* __restrict__ We, const float* __restrict__ be,
+                                  const float* __restrict__ W0, const float* __restrict__ b0, int T, int L, int D,
+                                  float* __restrict__ out, int Np) {
+  extern __shared__ float sh[];
+  float* temb = sh;       // [T]
+  float* emb = sh + T;    // [T]
+  const int i = blockIdx.x;
+  const int half = T / 2;
+  for (int s = threadIdx.x; s < T; s += blockDim.x) {
+    float v = 0.0f;
+    if (s < 2 * half) {
+      const int k = s < half ? s : s - half;
+      const float freq = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+      const float arg = static_cast<float>(i) * freq;
+      v = s < half ? cosf(arg) : sinf(arg);
+    }
+    temb[s] = v;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float acc = 0.0f;
+    for (int s = 0; s < T; ++s) acc = fmaf(We[static_cast<size_t>(t) * T + s], temb[s], acc);
+    emb[t] = acc + be[t];
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < Np; n += blockDim.x) {
+    float acc = 0.0f;
+    if (n < D) {
+      const float* w = W0 + static_cast<size_t>(n) * (L + T) + L;
+      for (int t = 0; t < T; ++t) acc = fmaf(w[t], emb[t], acc);
+      acc += b0[n];
+    }
+    out[static_cast<size_t>(i) * Np + n] = acc;
+  }
+}
+
+// coef[i] = {(1-a_i)/sqrt(1-ab_i), 1/sqrt(a_i), sqrt(b_i)*nd (0 at i=1), 0}  (train_SDRM.py:20-25,56)
+__global__ void coef_kernel(const float* __restrict__ sched, int T, float nd, float* __restrict__ coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > T) return;
+  const float b = sched[i], a = sched[(T + 1) + i], ab = sched[2 * (T + 1) + i];
+  float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i >= 1) {
+    c.x = (1.0f - a) / sqrtf(1.0f - ab);
+    c.y = 1.0f / sqrtf(a);
+    c.z = i > 1 ? sqrtf(b) * nd : 0.0f;
+  }
+  reinterpret_cast<float4*>(coef)[i] = c;
+}
+
+}  // namespace sdrm
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+using namespace sdrm;
+
+struct sdrm_handle {
+  int device = 0;
+  int num_sms = 0;
+  int last_launches = 0;
+  int* err_word = nullptr;
+  // denoiser
+  bool have_den = false;
+  int T = 0, L = 0, D = 0, nh = 0;
+  float nd = 1.0f;
+  Geom g0, gh, go;
+  uint8_t *w0 = nullptr, *wh = nullptr, *wo = nullptr;
+  float *bias0 = nullptr, *bh = nullptr, *bo = nullptr, *slopes = nullptr, *coef = nullptr;
+  // decoder
+  bool have_dec = false;
+  int H = 0, I = 0;
+  Geom g1, g2;
+  uint8_t *w1 = nullptr, *w2 = nullptr;
+  float *b1 = nullptr, *b2 = nullptr;
+};
+
+static void free_den(sdrm_handle* h) {
+  cudaFree(h->w0); cudaFree(h->wh); cudaFree(h->wo);
+  cudaFree(h->bias0); cudaFree(h->bh); cudaFree(h->bo); cudaFree(h->slopes); cudaFree(h->coef);
+  h->w0 = h->wh = h->wo = nullptr;
+  h->bias0 = h->bh = h->bo = h->slopes = h->coef = nullptr;
+  h->have_den = false;
+}
+static void free_dec(sdrm_handle* h) {
+  cudaFree(h->w1); cudaFree(h->w2); cudaFree(h->b1); cudaFree(h->b2);
+  h->w1 = h->w2 = nullptr;
+  h->b1 = h->b2 = nullptr;
+  h->have_dec = false;
+}
+
+static int engine_set_smem_attr() {
+  static bool done[64] = {false};
+  int dev = 0;
+  SDRM_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && done[dev]) return SDRM_OK;
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 ENGINE_SMEM_BYTES));
+  if (dev < 64) done[dev] = true;
+  return SDRM_OK;
+}
+
+static void launch_pack_weight(const float* W, int N, int K, long long ldw, int col_off, uint8_t* hi, uint8_t* lo,
+                               const Geom& g, cudaStream_t st) {
+  const long long total = static_cast<long long>(g.NCH) * g.KB * g.NC * 8;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 4096));
+  pack_weight_kernel<<<blocks, 256, 0, st>>>(W, N, K, ldw, col_off, hi, lo, g.NCH, g.NC, g.KB);
+}
+
+extern "C" {
+
+int sdrm_version(void) { return 100; }
+
+int sdrm_create(sdrm_handle** out, int device) {
+  if (!out) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_create: out is null");
+  SDRM_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SDRM_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "sdrm_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+             prop.major, prop.minor);
+    return sdrm_fail(SDRM_ERR_UNSUPPORTED, msg);
+  }
+  sdrm_handle* h = new sdrm_handle();
+  h->device = device;
+  h->num_sms = prop.multiProcessorCount;
+  SDRM_CUDA(cudaMalloc(&h->err_word, sizeof(int)));
+  SDRM_CUDA(cudaMemset(h->err_word, 0, sizeof(int)));
+  *out = h;
+  return SDRM_OK;
+}
+
+int sdrm_destroy(sdrm_handle* h) {
+  if (!h) return SDRM_OK;
+  cudaSetDevice(h->device);
+  free_den(h);
+  free_dec(h);
+  cudaFree(h->err_word);
+  delete h;
+  return SDRM_OK;
+}
+
+int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, const float* d_W0, const float* d_b0,
+                       const float* d_a0, const float* d_Wh, const float* d_bh, const float* d_ah, const float* d_Wo,
+                       const float* d_bo, const float* d_sched, int T, int L, int D, int nh, float noise_divider,
+                       void* stream) {
+  if (!h || !d_We || !d_be || !d_W0 || !d_b0 || !d_a0 || !d_Wo || !d_bo || !d_sched)
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: null pointer");
+  if (nh > 0 && (!d_Wh || !d_bh || !d_ah)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: nh>0 needs Wh,bh,ah");
+  if (T < 1 || L < 1 || D < 1 || nh < 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: bad shape");
+  if (2 + nh > MAX_STEP_LAYERS) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: nh > 6");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SDRM_CUDA(cudaSetDevice(h->device));
+  const bool same = h->have_den && h->T == T && h->L == L && h->D == D && h->nh == nh;
+  if (!same) {
+    free_den(h);
+    h->T = T; h->L = L; h->D = D; h->nh = nh;
+    h->g0 = make_geom(D, L);
+    h->gh = make_geom(D, D);
+    h->go = make_geom(L, D);
+    SDRM_CUDA(cudaMalloc(&h->w0, h->g0.img_bytes()));
+    SDRM_CUDA(cudaMalloc(&h->wh, h->gh.img_bytes()));
+    SDRM_CUDA(cudaMalloc(&h->wo, h->go.img_bytes()));
+    SDRM_CUDA(cudaMalloc(&h->bias0, sizeof(float) * (T + 1) * h->g0.Np));
+    SDRM_CUDA(cudaMalloc(&h->bh, sizeof(float) * h->gh.Np));
+    SDRM_CUDA(cudaMalloc(&h->bo, sizeof(float) * h->go.Np));
+    SDRM_CUDA(cudaMalloc(&h->slopes, sizeof(float) * 2));
+    SDRM_CUDA(cudaMalloc(&h->coef, sizeof(float) * 4 * (T + 1)));
+  }
+  h->nd = noise_divider;
+  launch_pack_weight(d_W0, D, L, L + T, 0, h->w0, nullptr, h->g0, st);
+  if (nh > 0) launch_pack_weight(d_Wh, D, D, D, 0, h->wh, nullptr, h->gh, st);
+  launch_pack_weight(d_Wo, L, D, D, 0, h->wo, nullptr, h->go, st);
+  bias_table_kernel<<<T + 1, 256, sizeof(float) * 2 * T, st>>>(d_We, d_be, d_W0, d_b0, T, L, D, h->bias0, h->g0.Np);
+  pad_bias_kernel<<<(h->gh.Np + 255) / 256, 256, 0, st>>>(nh > 0 ? d_bh : nullptr, D, h->bh, h->gh.Np);
+  pad_bias_kernel<<<(h->go.Np + 255) / 256, 256, 0, st>>>(d_bo, L, h->bo, h->go.Np);
+  SDRM_CUDA(cudaMemcpyAsync(h->slopes, d_a0, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (nh > 0) SDRM_CUDA(cudaMemcpyAsync(h->slopes + 1, d_ah, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  coef_kernel<<<(T + 1 + 127) / 128, 128, 0, st>>>(d_sched, T, noise_divider, h->coef);
+  SDRM_CUDA(cudaGetLastError());
+  h->have_den = true;
+  return SDRM_OK;
+}
+
+int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, const float* d_W2, const float* d_b2,
+                      int L, int H, int I, void* stream) {
+  if (!h || !d_W1 || !d_b1 || !d_W2 || !d_b2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: null pointer");
+  if (L < 1 || H < 1 || I < 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: bad shape");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SDRM_CUDA(cudaSetDevice(h->device));
+  const bool same = h->have_dec && h->g1.K == L && h->H == H && h->I == I;
+  if (!same) {
+    free_dec(h);
+    h->H = H; h->I = I;
+    h->g1 = make_geom(H, L);
+    h->g2 = make_geom(I, H);
+    SDRM_CUDA(cudaMalloc(&h->w1, 2 * h->g1.img_bytes()));
+    SDRM_CUDA(cudaMalloc(&h->w2, 2 * h->g2.img_bytes()));
+    SDRM_CUDA(cudaMalloc(&h->b1, sizeof(float) * h->g1.Np));
+    SDRM_CUDA(cudaMalloc(&h->b2, sizeof(float) * h->g2.Np));
+  }
+  launch_pack_weight(d_W1, H, L, L, 0, h->w1, h->w1 + h->g1.img_bytes(), h->g1, st);
+  launch_pack_weight(d_W2, I, H, H, 0, h->w2, h->w2 + h->g2.img_bytes(), h->g2, st);
+  pad_bias_kernel<<<(h->g1.Np + 255) / 256, 256, 0, st>>>(d_b1, H, h->b1, h->g1.Np);
+  pad_bias_kernel<<<(h->g2.Np + 255) / 256, 256, 0, st>>>(d_b2, I, h->b2, h->g2.Np);
+  SDRM_CUDA(cudaGetLastError());
+  h->have_dec = true;
+  return SDRM_OK;
+}
+
+static int kb_max_of(const sdrm_handle* h) {
+  int kb = 1;
+  const Geom* gs[5] = {&h->g0, &h->gh, &h->go, &h->g1, &h->g2};
+  for (int i = 0; i < 4; ++i) {  // g2 writes logits, not activations
+    kb = std::max(kb, gs[i]->KB);
+    kb = std::max(kb, (gs[i]->Np + KBLK - 1) / KBLK);
+  }
+  kb = std::max(kb, h->g2.KB);
+  return kb;
+}
+
+static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* act_bytes, size_t* stride) {
+  const long long n_tiles = (n + TILE_M - 1) / TILE_M;
+  *grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, h->num_sms)));
+  *act_bytes = static_cast<size_t>(kb_max_of(h)) * A_TILE_BYTES;
+  const int Lg16 = (h->L + 15) / 16;
+  const size_t xs = static_cast<size_t>(Lg16) * 4 * TILE_M * 16;
+  *stride = NUM_ACT_BUFS * (*act_bytes) + xs;
+}
+
+size_t sdrm_sample_workspace_bytes(const sdrm_handle* h, int64_t n) {
+  if (!h || !h->have_den || !h->have_dec || n <= 0) return 0;
+  int grid; size_t act, stride;
+  sample_geometry(h, n, &grid, &act, &stride);
+  return static_cast<size_t>(grid) * stride;
+}
+
+int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_t_start, uint64_t seed,
+                float* d_x0_out, float* d_logits, int64_t ld_logits, const float* d_inj_xT, const float* d_inj_z,
+                const uint8_t* d_inj_mask, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: null handle");
+  if (!h->have_den || !h->have_dec) return sdrm_fail(SDRM_ERR_STATE, "sdrm_sample: pack denoiser and decoder first");
+  if (h->g1.K != h->L) return sdrm_fail(SDRM_ERR_STATE, "sdrm_sample: decoder latent dim != denoiser latent dim");
+  if (n <= 0) return SDRM_OK;
+  if (!d_logits || ld_logits < h->I) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: logits buffer / ld");
+  if (!d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: null workspace");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SDRM_CUDA(cudaSetDevice(h->device));
+  int grid; size_t act, stride;
+  sample_geometry(h, n, &grid, &act, &stride);
+  if (workspace_bytes < static_cast<size_t>(grid) * stride) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small");
+  int rc = engine_set_smem_attr();
+  if (rc) return rc;
+
+  ChainParams P;
+  memset(&P, 0, sizeof P);
+  auto fill = [](LayerDesc& d, const uint8_t* w, const float* bias, const float* slope, int bstride, const Geom& g,
+                 int passes, int kind, int in_hi, int in_lo, int out_hi, int out_lo) {
+    d.w_img = w; d.bias = bias; d.slope = slope; d.bias_step_stride = bstride;
+    d.KB = g.KB; d.kmma_last = g.kmma_last; d.passes = passes; d.NCH = g.NCH; d.NC = g.NC; d.kind = kind;
+    d.in_hi = in_hi; d.in_lo = in_lo; d.out_hi = out_hi; d.out_lo = out_lo; d.n_valid = g.N;
+  };
+  int l = 0;
+  fill(P.step[l++], h->w0, h->bias0, h->slopes, h->g0.Np, h->g0, 1, EPI_PRELU, 2, 2, 0, 0);
+  for (int j = 0; j < h->nh; ++j)
+    fill(P.step[l++], h->wh, h->bh, h->slopes + 1, 0, h->gh, 1, EPI_PRELU, j & 1, j & 1, (j + 1) & 1, (j + 1) & 1);
+  fill(P.step[l++], h->wo, h->bo, nullptr, 0, h->go, 1, EPI_POSTERIOR, h->nh & 1, h->nh & 1, 2, 3);
+  P.n_step = l;
+  fill(P.dec[0], h->w1, h->b1, nullptr, 0, h->g1, 3, EPI_TANH_SPLIT, 2, 3, 0, 1);
+  fill(P.dec[1], h->w2, h->b2, nullptr, 0, h->g2, 3, EPI_LINEAR_OUT, 0, 1, 0, 0);
+  P.n_dec = 2;
+  P.T = h->T; P.L = h->L; P.Lg16 = (h->L + 15) / 16;
+  P.preloaded_input = 0;
+  P.n_rows = n; P.row_offset = row_offset;
+  P.coef = h->coef;
+  P.t_start = d_t_start;
+  P.x0_out = d_x0_out;
+  P.logits = d_logits; P.ld_logits = ld_logits;
+  P.inj_xT = d_inj_xT; P.inj_z = d_inj_z; P.inj_mask = d_inj_mask;
+  P.seed = seed;
+  P.scratch = static_cast<uint8_t*>(d_workspace);
+  P.scratch_stride = stride;
+  P.act_buf_bytes = act;
+  P.err_word = h->err_word;
+  sdrm_layer_engine_kernel<<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
+  SDRM_CUDA(cudaGetLastError());
+  h->last_launches = 1;
+  return SDRM_OK;
+}
+
+int sdrm_last_launch_count(const sdrm_handle* h) { return h ? h->last_launches : 0; }
+
+int sdrm_check_device_error(sdrm_handle* h, void* stream) {
+  if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "null handle");
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  int word = 0;
+  cudaError_t e2 = cudaMemcpy(&word, h->err_word, sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess || e2 != cudaSuccess || word != 0) {
+    char msg[200];
+    snprintf(msg, sizeof msg, "device error: sync=%s copy=%s watchdog=%d", cudaGetErrorString(e),
+             cudaGetErrorString(e2), word);
+    return sdrm_fail(SDRM_ERR_CUDA, msg);
+  }
+  return SDRM_OK;
+}
+
+// ---- probe: one dense layer through the engine -------------------------------------------------
+static void probe_geometry(int64_t M, int K, int N, Geom* g, size_t* act, size_t* w_off, size_t* b_off,
+                           size_t* s_off, size_t* total) {
+  *g = make_geom(N, K);
+  *act = static_cast<size_t>(g->KB) * A_TILE_BYTES;
+  const long long n_tiles = (M + TILE_M - 1) / TILE_M;
+  size_t off = 256;  // err word
+  *w_off = off; off += 2 * g->img_bytes();
+  *b_off = off; off += sizeof(float) * g->Np; off = (off + 1023) & ~static_cast<size_t>(1023);
+  *s_off = off; off += static_cast<size_t>(n_tiles) * 2 * (*act);
+  *total = off;
+}
+
+size_t sdrm_probe_linear_workspace_bytes(int64_t M, int K, int N) {
+  if (M <= 0 || K <= 0 || N <= 0) return 0;
+  Geom g; size_t act, w, b, s, total;
+  probe_geometry(M, K, N, &g, &act, &w, &b, &s, &total);
+  return total;
+}
+
+int sdrm_probe_linear(const float* d_A, const float* d_W, const float* d_bias, float* d_out, int64_t M, int K, int N,
+                      int split3, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_A || !d_W || !d_out || !d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_probe_linear: null pointer");
+  if (M <= 0 || K <= 0 || N <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_probe_linear: bad shape");
+  Geom g; size_t act, w_off, b_off, s_off, total;
+  probe_geometry(M, K, N, &g, &act, &w_off, &b_off, &s_off, &total);
+  if (workspace_bytes < total) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_probe_linear: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = engine_set_smem_attr();
+  if (rc) return rc;
+  int dev = 0, sms = 0;
+  SDRM_CUDA(cudaGetDevice(&dev));
+  SDRM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  uint8_t* ws = static_cast<uint8_t*>(d_workspace);
+  SDRM_CUDA(cudaMemsetAsync(ws, 0, 256, st));
+  launch_pack_weight(d_W, N, K, K, 0, ws + w_off, ws + w_off + g.img_bytes(), g, st);
+  pad_bias_kernel<<<(g.Np + 255) / 256, 256, 0, st>>>(d_bias, N, reinterpret_cast<float*>(ws + b_off), g.Np);
+  const long long n_tiles = (M + TILE_M - 1) / TILE_M;
+  {
+    const long long total_chunks = n_tiles * g.KB * TILE_M * 8;
+    const int blocks = static_cast<int>(std::min<long long>((total_chunks + 255) / 256, 8192));
+    pack_act_kernel<<<blocks, 256, 0, st>>>(d_A, M, K, ws + s_off, 2 * act, act, g.KB);
+  }
+  ChainParams P;
+  memset(&P, 0, sizeof P);
+  LayerDesc& d = P.dec[0];
+  d.w_img = ws + w_off; d.bias = reinterpret_cast<const float*>(ws + b_off); d.slope = nullptr;
+  d.bias_step_stride = 0; d.KB = g.KB; d.kmma_last = g.kmma_last; d.passes = split3 ? 3 : 1;
+  d.NCH = g.NCH; d.NC = g.NC; d.kind = EPI_LINEAR_OUT; d.in_hi = 0; d.in_lo = 1; d.out_hi = 0; d.out_lo = 0;
+  d.n_valid = N;
+  P.n_step = 0; P.n_dec = 1; P.T = 0; P.L = K; P.Lg16 = 0; P.preloaded_input = 1;
+  P.n_rows = M; P.row_offset = 0;
+  P.logits = d_out; P.ld_logits = N;
+  P.scratch = ws + s_off; P.scratch_stride = 2 * act; P.act_buf_bytes = act;
+  P.err_word = reinterpret_cast<int*>(ws);
+  const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, sms)));
+  sdrm_layer_engine_kernel<<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,440 @@
+// K1 — streaming tcgen05 layer engine for the SDRM reverse-diffusion chain and VAE decode.
+//
+// Replaces the reference's per-step eager op chain (sample_ddpm, train_SDRM.py:50-61; SDRM.forward
+// 97-103; denoise_add_noise 20-25; VAE.decode 252-254) with ONE persistent kernel:
+//   * a CTA owns a 128-row tile of users for the whole T-step chain and the decode;
+//   * every dense layer is a tcgen05 (UMMA) GEMM: A = bf16 activations, B = bf16 weights, both
+//     stored in global memory as pre-swizzled "tile images" that one cp.async.bulk (TMA bulk engine)
+//     drops straight into the 128B-swizzled shared-memory operand layout; accumulators live in TMEM
+//     (2 x 256 columns, double-buffered so the epilogue of chunk c overlaps the UMMAs of chunk c+1);
+//   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
+//     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the
+//     bf16 (or bf16 hi/lo) re-quantisation, and write the next layer's A images (L2-resident scratch);
+//   * warp 0 = TMA producer, warp 1 = UMMA issuer (one elected thread), warps 2-5 = epilogue.
+// Rows are independent, so there is no inter-CTA synchronisation anywhere.
+#include "layer_engine.cuh"
+#include "philox.cuh"
+#include "ptx_sm100.cuh"
+
+namespace sdrm {
+
+namespace {
+
+struct SmemLayout {
+  uint32_t stage_a[NUM_STAGES];
+  uint32_t stage_w[NUM_STAGES];
+  uint32_t full[NUM_STAGES];
+  uint32_t empty[NUM_STAGES];
+  uint32_t acc_full[2];
+  uint32_t acc_empty[2];
+  uint32_t act_ready;
+  uint32_t tile_ready;
+};
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// write 16 consecutive bf16 features [f0, f0+16) of tile row r into a k-block image buffer
+__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8]) {
+  const int kb = f0 >> 6;
+  const int j0 = (f0 & 63) >> 3;
+  uint8_t* base = buf + static_cast<size_t>(kb) * A_TILE_BYTES + r * 128;
+  const int sw = r & 7;
+  *reinterpret_cast<uint4*>(base + ((j0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(base + (((j0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// fp32 state layout inside a tile: [16-col group][float4 index 0..3][row 0..127][4 floats]
+__device__ __forceinline__ float4* xstate_ptr(float* xs, int g16, int j, int r) {
+  return reinterpret_cast<float4*>(xs) + (static_cast<size_t>(g16) * 4 + j) * TILE_M + r;
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base_addr - raw_addr);
+
+  SmemLayout S;
+#pragma unroll
+  for (int s = 0; s < NUM_STAGES; ++s) {
+    S.stage_a[s] = base_addr + s * STAGE_BYTES;
+    S.stage_w[s] = S.stage_a[s] + A_TILE_BYTES;
+  }
+  const uint32_t bar_base = base_addr + NUM_STAGES * STAGE_BYTES;
+#pragma unroll
+  for (int s = 0; s < NUM_STAGES; ++s) {
+    S.full[s] = bar_base + 8 * s;
+    S.empty[s] = bar_base + 8 * (NUM_STAGES + s);
+  }
+  S.acc_full[0] = bar_base + 8 * (2 * NUM_STAGES + 0);
+  S.acc_full[1] = bar_base + 8 * (2 * NUM_STAGES + 1);
+  S.acc_empty[0] = bar_base + 8 * (2 * NUM_STAGES + 2);
+  S.acc_empty[1] = bar_base + 8 * (2 * NUM_STAGES + 3);
+  S.act_ready = bar_base + 8 * (2 * NUM_STAGES + 4);
+  S.tile_ready = bar_base + 8 * (2 * NUM_STAGES + 5);
+  uint8_t* misc = smem + NUM_STAGES * STAGE_BYTES + 8 * (2 * NUM_STAGES + 6);
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
+  volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
+  volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x 4 ints
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NUM_STAGES; ++s) {
+      mbar_init(S.full[s], 1);
+      mbar_init(S.empty[s], 1);
+    }
+    mbar_init(S.acc_full[0], 1);
+    mbar_init(S.acc_full[1], 1);
+    mbar_init(S.acc_empty[0], 4);
+    mbar_init(S.acc_empty[1], 4);
+    mbar_init(S.act_ready, 4);
+    mbar_init(S.tile_ready, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long n_tiles = (P.n_rows + TILE_M - 1) / TILE_M;
+  int* err = P.err_word;
+
+  auto scratch_of = [&](long long tile) -> uint8_t* {
+    const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x);
+    return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
+  };
+
+  if (warp == 0) {
+    // ======================================= TMA producer =======================================
+    if (lane == 0) {
+      uint32_t stage = 0, sphase = 0, act_par = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(S.tile_ready, it & 1, err, WD_PRODUCER_TILE);
+        const int T_tile = tile_T[it & 1];
+        const uint8_t* sc = scratch_of(tile);
+        bool first = true;
+        auto run = [&](const LayerDesc& ld) {
+          if (!first) {
+            mbar_wait(S.act_ready, act_par, err, WD_PRODUCER_ACT);
+            act_par ^= 1;
+          }
+          first = false;
+          const uint8_t* a_hi = sc + static_cast<size_t>(ld.in_hi) * P.act_buf_bytes;
+          const uint8_t* a_lo = sc + static_cast<size_t>(ld.in_lo) * P.act_buf_bytes;
+          const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;
+          for (int c = 0; c < ld.NCH; ++c) {
+            for (int p = 0; p < ld.passes; ++p) {
+              const uint8_t* a_src = (p == 2) ? a_lo : a_hi;
+              const int which = (p == 1) ? 1 : 0;
+              const uint8_t* w_src = ld.w_img + (static_cast<size_t>(which) * ld.NCH + c) * ld.KB * w_bytes;
+              for (int kb = 0; kb < ld.KB; ++kb) {
+                mbar_wait(S.empty[stage], sphase ^ 1, err, WD_PRODUCER_EMPTY);
+                mbar_arrive_expect_tx(S.full[stage], A_TILE_BYTES + w_bytes);
+                bulk_g2s(S.stage_a[stage], a_src + static_cast<size_t>(kb) * A_TILE_BYTES, A_TILE_BYTES, S.full[stage]);
+                bulk_g2s(S.stage_w[stage], w_src + static_cast<size_t>(kb) * w_bytes, w_bytes, S.full[stage]);
+                if (++stage == NUM_STAGES) { stage = 0; sphase ^= 1; }
+              }
+            }
+          }
+        };
+        for (int i = T_tile; i >= 1; --i)
+          for (int l = 0; l < P.n_step; ++l) run(P.step[l]);
+        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
+      }
+    }
+  } else if (warp == 1) {
+    // ======================================= UMMA issuer ========================================
+    if (lane == 0) {
+      uint32_t stage = 0, sphase = 0, cc = 0;
+      int it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(S.tile_ready, it & 1, err, WD_MMA_TILE);
+        const int T_tile = tile_T[it & 1];
+        auto run = [&](const LayerDesc& ld) {
+          const uint32_t idesc = umma_idesc_bf16(TILE_M, ld.NC);
+          for (int c = 0; c < ld.NCH; ++c) {
+            const uint32_t buf = cc & 1u;
+            mbar_wait(S.acc_empty[buf], ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * 256u;
+            uint32_t acc = 0;
+            for (int p = 0; p < ld.passes; ++p) {
+              for (int kb = 0; kb < ld.KB; ++kb) {
+                mbar_wait(S.full[stage], sphase, err, WD_MMA_FULL);
+                tc_fence_after();
+                const uint64_t a_desc = umma_desc_sw128(S.stage_a[stage]);
+                const uint64_t b_desc = umma_desc_sw128(S.stage_w[stage]);
+                const int nk = (kb == ld.KB - 1) ? ld.kmma_last : 4;
+                for (int k = 0; k < nk; ++k) {
+                  // +32 B (16 bf16) along K inside the swizzle row = +2 in the 16-byte address field
+                  umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
+                  acc = 1;
+                }
+                umma_commit(S.empty[stage]);
+                if (++stage == NUM_STAGES) { stage = 0; sphase ^= 1; }
+              }
+            }
+            umma_commit(S.acc_full[buf]);
+            ++cc;
+          }
+        };
+        for (int i = T_tile; i >= 1; --i)
+          for (int l = 0; l < P.n_step; ++l) run(P.step[l]);
+        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
+      }
+    }
+  } else {
+    // ======================================= epilogue warps =====================================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;            // tile row owned by this thread
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t cc = 0;
+    int it = 0;
+
+    // zero the activation buffers once: K-padding columns must read as exact zeros
+    if (!P.preloaded_input) {
+      uint4* z = reinterpret_cast<uint4*>(scratch_of(blockIdx.x));
+      const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
+      for (size_t i = threadIdx.x - 64; i < n16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+      epi_bar_sync();
+    }
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      uint8_t* sc = scratch_of(tile);
+      float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+      const long long row = tile * TILE_M + r;
+      const bool valid = row < P.n_rows;
+      const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
+      int t_row = P.T;
+      if (P.t_start) t_row = valid ? P.t_start[row] : 0;
+
+      // ---- tile start step = max over rows
+      int m = t_row;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (lane == 0) warp_max[(it & 1) * 4 + q] = m;
+      epi_bar_sync();
+      int T_tile = max(max(warp_max[(it & 1) * 4 + 0], warp_max[(it & 1) * 4 + 1]),
+                       max(warp_max[(it & 1) * 4 + 2], warp_max[(it & 1) * 4 + 3]));
+      if (P.n_step == 0) T_tile = 0;
+
+      auto keep_mask16 = [&](int step, int g16) -> uint32_t {
+        // bit b = keep flag of column 16*g16 + b at this step (F.dropout p = .5, train_SDRM.py:100)
+        if (!valid) return 0u;
+        if (P.inj_mask) {
+          uint32_t bits = 0;
+          const uint8_t* mp = P.inj_mask + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int f = g16 * 16 + e;
+            if (f < P.L && mp[f]) bits |= (1u << e);
+          }
+          return bits;
+        }
+        return philox_mask16(P.seed, STREAM_MASK, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16));
+      };
+
+      // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38)
+      if (P.n_step > 0) {
+        uint8_t* in0 = sc + static_cast<size_t>(P.step[0].in_hi) * P.act_buf_bytes;
+        for (int g = 0; g < P.Lg16; ++g) {
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float z4[4];
+            if (P.inj_xT) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int f = g * 16 + j * 4 + e;
+                z4[e] = (valid && f < P.L) ? P.inj_xT[static_cast<size_t>(row) * P.L + f] : 0.0f;
+              }
+            } else {
+              philox_normal4(P.seed, STREAM_NORMAL, grow, 0u, static_cast<uint32_t>(g * 4 + j), z4);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int f = g * 16 + j * 4 + e;
+              x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;
+            }
+            *xstate_ptr(xs, g, j, r) = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+          }
+          const uint32_t keep = keep_mask16(T_tile, g);
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float a0 = ((keep >> (2 * e)) & 1u) ? 2.0f * x[2 * e] : 0.0f;
+            const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * x[2 * e + 1] : 0.0f;
+            pk[e] = pack_bf16x2(a0, a1);
+          }
+          store_act16(in0, r, g * 16, pk);
+        }
+      }
+      if (q == 0 && lane == 0) tile_T[it & 1] = T_tile;
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(S.tile_ready);
+
+      // ---- layers
+      auto run = [&](const LayerDesc& ld, int step, bool last_of_tile) {
+        uint8_t* out_hi = sc + static_cast<size_t>(ld.out_hi) * P.act_buf_bytes;
+        uint8_t* out_lo = sc + static_cast<size_t>(ld.out_lo) * P.act_buf_bytes;
+        const float* bias_row = ld.bias + static_cast<size_t>(step) * ld.bias_step_stride;
+        const float slope = ld.slope ? __ldg(ld.slope) : 0.0f;
+        float c1 = 0.f, c2 = 0.f, sg = 0.f;
+        if (ld.kind == EPI_POSTERIOR) {
+          const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
+          c1 = cf.x; c2 = cf.y; sg = cf.z;
+        }
+        const bool active = step <= t_row;
+        for (int c = 0; c < ld.NCH; ++c) {
+          const uint32_t buf = cc & 1u;
+          mbar_wait(S.acc_full[buf], (cc >> 1) & 1u, err, WD_EPI_ACC);
+          tc_fence_after();
+          const int ngroups = ld.NC >> 4;
+          for (int g = 0; g < ngroups; ++g) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
+            tmem_ld_wait();
+            const int f0 = c * ld.NC + g * 16;
+            float h[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + f0) + j);
+              h[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
+              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+            }
+            if (ld.kind == EPI_PRELU) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float a0 = h[2 * e] > 0.f ? h[2 * e] : slope * h[2 * e];
+                const float a1 = h[2 * e + 1] > 0.f ? h[2 * e + 1] : slope * h[2 * e + 1];
+                pk[e] = pack_bf16x2(a0, a1);
+              }
+              store_act16(out_hi, r, f0, pk);
+            } else if (ld.kind == EPI_POSTERIOR) {
+              // x_{i-1} = (x_i - eps * (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) * nd * z
+              const int g16 = f0 >> 4;
+              if (g16 < P.Lg16) {
+                float xn[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 xo = *xstate_ptr(xs, g16, j, r);
+                  float z4[4] = {0.f, 0.f, 0.f, 0.f};
+                  if (sg != 0.0f && valid) {
+                    if (P.inj_z) {
+                      const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
+#pragma unroll
+                      for (int e = 0; e < 4; ++e) {
+                        const int f = f0 + 4 * j + e;
+                        z4[e] = f < P.L ? zp[f] : 0.0f;
+                      }
+                    } else {
+                      philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step),
+                                     static_cast<uint32_t>(g16 * 4 + j), z4);
+                    }
+                  }
+                  const float xv[4] = {xo.x, xo.y, xo.z, xo.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const int f = f0 + 4 * j + e;
+                    const float eps = fast_tanh(h[4 * j + e]);
+                    float nv = (xv[e] - eps * c1) * c2 + sg * z4[e];
+                    nv = active ? nv : xv[e];
+                    xn[4 * j + e] = (valid && f < P.L) ? nv : 0.0f;
+                  }
+                  *xstate_ptr(xs, g16, j, r) = make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]);
+                }
+                if (step > 1) {
+                  const uint32_t keep = keep_mask16(step - 1, g16);
+                  uint32_t pk[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float a0 = ((keep >> (2 * e)) & 1u) ? 2.0f * xn[2 * e] : 0.0f;
+                    const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * xn[2 * e + 1] : 0.0f;
+                    pk[e] = pack_bf16x2(a0, a1);
+                  }
+                  store_act16(out_hi, r, f0, pk);
+                } else {
+                  // last reverse step: hand x_0 to the decoder as bf16 hi/lo (bf16x3 GEMM)
+                  uint32_t ph[8], pl[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const float h0 = bf16_round(xn[2 * e]), h1 = bf16_round(xn[2 * e + 1]);
+                    ph[e] = pack_bf16x2(h0, h1);
+                    pl[e] = pack_bf16x2(xn[2 * e] - h0, xn[2 * e + 1] - h1);
+                  }
+                  store_act16(out_hi, r, f0, ph);
+                  store_act16(out_lo, r, f0, pl);
+                  if (P.x0_out && valid) {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e)
+                      if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = xn[e];
+                  }
+                }
+              }
+            } else if (ld.kind == EPI_TANH_SPLIT) {
+              uint32_t ph[8], pl[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float t0 = fast_tanh(h[2 * e]), t1 = fast_tanh(h[2 * e + 1]);
+                const float h0 = bf16_round(t0), h1 = bf16_round(t1);
+                ph[e] = pack_bf16x2(h0, h1);
+                pl[e] = pack_bf16x2(t0 - h0, t1 - h1);
+              }
+              store_act16(out_hi, r, f0, ph);
+              store_act16(out_lo, r, f0, pl);
+            } else {  // EPI_LINEAR_OUT
+              if (valid) {
+                float* orow = P.logits + static_cast<size_t>(row) * P.ld_logits;
+                if (((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0) &&
+                    (f0 + 16 <= ld.n_valid)) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j)
+                    reinterpret_cast<float4*>(orow + f0)[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 16; ++e)
+                    if (f0 + e < ld.n_valid) orow[f0 + e] = h[e];
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(S.acc_empty[buf]);
+          ++cc;
+        }
+        if (!last_of_tile) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(S.act_ready);
+        }
+      };
+      for (int i = T_tile; i >= 1; --i)
+        for (int l = 0; l < P.n_step; ++l) run(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1));
+      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l == P.n_dec - 1);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace sdrm

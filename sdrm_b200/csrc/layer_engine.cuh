@@ -1,0 +1,63 @@
+// Shared definitions of the streaming tcgen05 layer engine (kernel K1).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+namespace sdrm {
+
+constexpr int TILE_M = 128;                        // rows of users per CTA tile (UMMA M)
+constexpr int KBLK = 64;                           // bf16 elements per 128-byte swizzle row
+constexpr int A_TILE_BYTES = TILE_M * 128;         // one activation k-block image: 128 rows x 128 B
+constexpr int MAX_NC = 256;                        // widest UMMA N
+constexpr int W_TILE_BYTES_MAX = MAX_NC * 128;     // one weight k-block image
+constexpr int STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES_MAX;
+constexpr int NUM_STAGES = 4;
+constexpr int MAX_STEP_LAYERS = 8;                 // 2 + nh, nh <= 6
+constexpr int NUM_ACT_BUFS = 4;
+constexpr int ENGINE_THREADS = 192;                // warp0 TMA, warp1 UMMA, warps 2-5 epilogue
+constexpr int ENGINE_SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
+
+// error codes the device watchdog writes (which wait timed out)
+enum : int { WD_PRODUCER_EMPTY = 101, WD_PRODUCER_ACT = 102, WD_PRODUCER_TILE = 103, WD_MMA_FULL = 201,
+             WD_MMA_ACC = 202, WD_MMA_TILE = 203, WD_EPI_ACC = 301 };
+
+struct LayerDesc {
+  const uint8_t* w_img;   // weight images [which: hi, lo][chunk][k block][NC rows x 128 B], 128B-swizzled
+  const float* bias;      // [bias rows][Np]
+  const float* slope;     // PReLU slope (device scalar) or nullptr
+  int bias_step_stride;   // floats between the bias rows of consecutive diffusion steps (0: constant)
+  int KB;                 // 64-wide k blocks per pass
+  int kmma_last;          // UMMAs (K = 16 each) issued for the last k block, 1..4
+  int passes;             // 1 = bf16, 3 = bf16x3 split (hi*hi + hi*lo + lo*hi)
+  int NCH, NC;            // N chunks and chunk width (multiple of 16, <= 256)
+  int kind;               // EpiKind
+  int in_hi, in_lo;       // activation buffers read (lo only when passes == 3)
+  int out_hi, out_lo;     // activation buffers written
+  int n_valid;            // real output features
+};
+
+struct ChainParams {
+  LayerDesc step[MAX_STEP_LAYERS];
+  LayerDesc dec[2];
+  int n_step, n_dec;
+  int T, L, Lg16;         // Lg16 = ceil(L / 16) column groups of the fp32 state
+  int preloaded_input;    // probe mode: activation images were packed per TILE by the host
+  long long n_rows, row_offset;
+  const float* coef;      // [T+1][4] = c1, c2, sigma*nd, 0   (denoise_add_noise, train_SDRM.py:20-25)
+  const int32_t* t_start; // per-row start step or nullptr
+  float* x0_out;          // [n, L] or nullptr
+  float* logits;          // [n, ld_logits]
+  long long ld_logits;
+  const float* inj_xT;    // [n, L]
+  const float* inj_z;     // [T+1, n, L]
+  const uint8_t* inj_mask;// [T+1, n, L]
+  unsigned long long seed;
+  uint8_t* scratch;       // per-CTA (or per-tile in probe mode) scratch
+  size_t scratch_stride;  // bytes per CTA
+  size_t act_buf_bytes;   // bytes of one activation buffer (KBmax * A_TILE_BYTES)
+  int* err_word;
+};
+
+}  // namespace sdrm

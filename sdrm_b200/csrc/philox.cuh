@@ -1,0 +1,73 @@
+// Counter-based Philox4x32-10 (Salmon et al., SC'11) and the SDRM noise streams built on it.
+// The same arithmetic is restated in oracle/philox_ref.py; tests pin one against the other.
+//
+// Stream layout (key = 64-bit seed, counter = {c0, c1, c2, c3}):
+//   normals : c0 = column / 4, c1 = step, c2 = global row (low 32), c3 = STREAM_NORMAL | (row >> 32) << 8
+//             -> 4 x u32 -> two Box-Muller pairs -> N(0,1) for columns 4*c0 .. 4*c0+3
+//             step 0 is x_T; step i >= 2 is the z of reverse step i (train_SDRM.py:51,56)
+//   dropout : c0 = column / 16, c1 = step, c2 = row, c3 = STREAM_MASK | ...
+//             -> keep bit of column (16*c0 + b) is bit b of word 0   (F.dropout p = 0.5, train_SDRM.py:100)
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace sdrm {
+
+enum : uint32_t { STREAM_NORMAL = 0u, STREAM_MASK = 1u, STREAM_TRAIN_NOISE = 2u, STREAM_TRAIN_MASK = 3u };
+
+struct u32x4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+    uint64_t p0 = static_cast<uint64_t>(M0) * c0, p1 = static_cast<uint64_t>(M1) * c2;
+    uint32_t hi0 = static_cast<uint32_t>(p0 >> 32), lo0 = static_cast<uint32_t>(p0);
+    uint32_t hi1 = static_cast<uint32_t>(p1 >> 32), lo1 = static_cast<uint32_t>(p1);
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n1 = lo1;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    uint32_t n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  return u32x4{c0, c1, c2, c3};
+}
+
+#ifdef __CUDACC__
+// Box-Muller on 24-bit uniforms: u1 in (0,1], u2 in [0,1)
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float u1 = static_cast<float>((a >> 8) + 1u) * 5.9604644775390625e-8f;  // 2^-24
+  float u2 = static_cast<float>(b >> 8) * 5.9604644775390625e-8f;
+  float r = sqrtf(-2.0f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  z0 = r * c;
+  z1 = r * s;
+}
+__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream, uint64_t row, uint32_t step,
+                                               uint32_t col_quad, float (&z)[4]) {
+  u32x4 r = philox4x32_10(col_quad, step, static_cast<uint32_t>(row),
+                          stream | (static_cast<uint32_t>(row >> 32) << 8), static_cast<uint32_t>(seed),
+                          static_cast<uint32_t>(seed >> 32));
+  box_muller(r.x, r.y, z[0], z[1]);
+  box_muller(r.z, r.w, z[2], z[3]);
+}
+__device__ __forceinline__ uint32_t philox_mask16(uint64_t seed, uint32_t stream, uint64_t row, uint32_t step,
+                                                  uint32_t col_group16) {
+  u32x4 r = philox4x32_10(col_group16, step, static_cast<uint32_t>(row),
+                          stream | (static_cast<uint32_t>(row >> 32) << 8), static_cast<uint32_t>(seed),
+                          static_cast<uint32_t>(seed >> 32));
+  return r.x & 0xFFFFu;
+}
+#endif
+
+}  // namespace sdrm

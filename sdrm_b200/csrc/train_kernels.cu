@@ -1,0 +1,209 @@
+// K2 — fused elementwise kernels of the diffusion training step (reference: train_SDRM.py:321-337,
+// perturb_input 202-203, score_matching_loss 191-199).  All three are HBM-bound streaming kernels:
+// vectorised (float4) coalesced reads, one pass, fp64 block reductions for the loss statistics.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdrm_b200.h"
+#include "host_util.h"
+#include "philox.cuh"
+
+namespace sdrm {
+
+// One thread = one group of 4 consecutive latent columns of one row.
+//   noise   = N(0,1) * nd                                  (train_SDRM.py:326)
+//   x_t     = sqrt(ab[t]) * mu + (1 - ab[t]) * noise       (train_SDRM.py:203 -- NOT sqrt on the noise term)
+//   x_p     = mu + mu_coef * noise                          (train_SDRM.py:194)
+//   in_k    = input_k * keep_k * 2                          (F.dropout p=.5 always on, train_SDRM.py:100)
+__global__ void __launch_bounds__(256) noise_inputs_kernel(
+    const float* __restrict__ mu, const long long* __restrict__ t, const float* __restrict__ ab, long long B, int L,
+    float nd, float mu_coef, unsigned long long seed, long long row_offset, const float* __restrict__ inj_noise,
+    const uint8_t* __restrict__ inj_masks, float* __restrict__ noise_out, float* __restrict__ in_pert,
+    float* __restrict__ in_clean, float* __restrict__ in_shift, uint8_t* __restrict__ masks_out) {
+  const int groups = (L + 3) >> 2;
+  const long long total = B * groups;
+  const bool vec = (L & 3) == 0;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = idx / groups;
+    const int g = static_cast<int>(idx - b * groups);
+    const int f0 = g * 4;
+    const size_t off = static_cast<size_t>(b) * L + f0;
+    const int nvalid = min(4, L - f0);
+    float m[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
+      const float4 v = *reinterpret_cast<const float4*>(mu + off);
+      m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
+    } else {
+      for (int e = 0; e < nvalid; ++e) m[e] = mu[off + e];
+    }
+    if (inj_noise) {
+      for (int e = 0; e < nvalid; ++e) nz[e] = inj_noise[off + e];
+    } else {
+      float z4[4];
+      philox_normal4(seed, STREAM_TRAIN_NOISE, static_cast<unsigned long long>(row_offset + b), 0u,
+                     static_cast<uint32_t>(g), z4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) nz[e] = z4[e] * nd;
+    }
+    const float abt = ab[t[b]];
+    const float sa = sqrtf(abt), om = 1.0f - abt;
+    uint32_t keep[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (inj_masks) {
+        keep[k] = 0;
+        for (int e = 0; e < nvalid; ++e)
+          keep[k] |= (inj_masks[(static_cast<size_t>(k) * B + b) * L + f0 + e] ? 1u : 0u) << e;
+      } else {
+        const uint32_t bits = philox_mask16(seed, STREAM_TRAIN_MASK, static_cast<unsigned long long>(row_offset + b),
+                                            static_cast<uint32_t>(k), static_cast<uint32_t>(f0 >> 4));
+        keep[k] = (bits >> (f0 & 15)) & 0xFu;
+      }
+    }
+    float xp[4], xc[4], xs[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float xt = sa * m[e] + om * nz[e];
+      const float xq = m[e] + mu_coef * nz[e];
+      xp[e] = ((keep[0] >> e) & 1u) ? 2.0f * xt : 0.0f;
+      xc[e] = ((keep[1] >> e) & 1u) ? 2.0f * m[e] : 0.0f;
+      xs[e] = ((keep[2] >> e) & 1u) ? 2.0f * xq : 0.0f;
+    }
+    if (vec) {
+      if (noise_out) *reinterpret_cast<float4*>(noise_out + off) = make_float4(nz[0], nz[1], nz[2], nz[3]);
+      *reinterpret_cast<float4*>(in_pert + off) = make_float4(xp[0], xp[1], xp[2], xp[3]);
+      *reinterpret_cast<float4*>(in_clean + off) = make_float4(xc[0], xc[1], xc[2], xc[3]);
+      *reinterpret_cast<float4*>(in_shift + off) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+    } else {
+      for (int e = 0; e < nvalid; ++e) {
+        if (noise_out) noise_out[off + e] = nz[e];
+        in_pert[off + e] = xp[e];
+        in_clean[off + e] = xc[e];
+        in_shift[off + e] = xs[e];
+      }
+    }
+    if (masks_out) {
+      for (int k = 0; k < 3; ++k)
+        for (int e = 0; e < nvalid; ++e)
+          masks_out[(static_cast<size_t>(k) * B + b) * L + f0 + e] = static_cast<uint8_t>((keep[k] >> e) & 1u);
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// stats += {sum r, sum r^2, sum (sd-r)^2, sum (r-sx)^2, count};  r = pred - mu, sd = (psx - sx)/mu_coef^2
+__global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict__ pred, const float* __restrict__ sx,
+                                                         const float* __restrict__ psx, const float* __restrict__ mu,
+                                                         long long count, float mu2, double* __restrict__ stats) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float r = pred[i] - mu[i];
+    const float sd = (psx[i] - sx[i]) / mu2;
+    const float d1 = sd - r, d2 = r - sx[i];
+    s0 += r;
+    s1 += static_cast<double>(r) * r;
+    s2 += static_cast<double>(d1) * d1;
+    s3 += static_cast<double>(d2) * d2;
+  }
+  __shared__ double sh[4][8];
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sh[0][w] = s0; sh[1][w] = s1; sh[2][w] = s2; sh[3][w] = s3; }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double a = 0;
+    for (int i = 0; i < 8; ++i) a += sh[threadIdx.x][i];
+    atomicAdd(stats + threadIdx.x, a);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(stats + 4, static_cast<double>(count));
+}
+
+// Analytic seeds of d loss / d {pred, sx, psx} from the GLOBAL statistics.
+__global__ void __launch_bounds__(256) loss_seeds_kernel(const float* __restrict__ pred, const float* __restrict__ sx,
+                                                         const float* __restrict__ psx, const float* __restrict__ mu,
+                                                         long long count, float mu2, const double* __restrict__ stats,
+                                                         float* __restrict__ g_pred, float* __restrict__ g_sx,
+                                                         float* __restrict__ g_psx, float* __restrict__ loss_out) {
+  const double N = stats[4];
+  const double mean_r = stats[0] / N;
+  const double V = (stats[1] - N * mean_r * mean_r) / (N - 1.0);
+  const double A = stats[2] / N, Bm = stats[3] / N;
+  const double den = 1e-8 + V;
+  const double c = 0.5 / den;
+  const double kvar = -0.5 * (A + Bm) / (den * den) * 2.0 / (N - 1.0);
+  const float two_c_over_N = static_cast<float>(2.0 * c / N);
+  const float kv = static_cast<float>(kvar), mr = static_cast<float>(mean_r);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) loss_out[0] = static_cast<float>(0.5 * (A + Bm) / den);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float r = pred[i] - mu[i];
+    const float sd = (psx[i] - sx[i]) / mu2;
+    const float d1 = sd - r, d2 = r - sx[i];
+    const float gsd = two_c_over_N * d1;
+    if (g_psx) g_psx[i] = gsd / mu2;
+    if (g_sx) g_sx[i] = -two_c_over_N * d2 - gsd / mu2;
+    if (g_pred) g_pred[i] = two_c_over_N * (d2 - d1) + kv * (r - mr);
+  }
+}
+
+}  // namespace sdrm
+
+using namespace sdrm;
+
+static int grid_for(long long work, int sms_mult = 8) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (work + 255) / 256;
+  long long cap = static_cast<long long>(sms) * sms_mult;  // multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+extern "C" {
+
+int sdrm_noise_inputs(const float* d_mu, const int64_t* d_t, const float* d_ab, int64_t B, int L, float noise_divider,
+                      double mu_coef, uint64_t seed, int64_t row_offset, const float* d_inj_noise,
+                      const uint8_t* d_inj_masks, float* d_noise_out, float* d_in_pert, float* d_in_clean,
+                      float* d_in_shift, uint8_t* d_masks_out, void* stream) {
+  if (!d_mu || !d_t || !d_ab || !d_in_pert || !d_in_clean || !d_in_shift)
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_noise_inputs: null pointer");
+  if (B <= 0 || L <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_noise_inputs: bad shape");
+  const long long total = B * ((L + 3) / 4);
+  noise_inputs_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_mu, reinterpret_cast<const long long*>(d_t), d_ab, B, L, noise_divider, static_cast<float>(mu_coef), seed, row_offset, d_inj_noise,
+      d_inj_masks, d_noise_out, d_in_pert, d_in_clean, d_in_shift, d_masks_out);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_loss_stats(const float* d_pred, const float* d_sx, const float* d_psx, const float* d_mu, int64_t count,
+                    double mu_coef, double* d_stats, void* stream) {
+  if (!d_pred || !d_sx || !d_psx || !d_mu || !d_stats) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_loss_stats: null pointer");
+  if (count <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_loss_stats: count <= 0");
+  loss_stats_kernel<<<grid_for(count, 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_pred, d_sx, d_psx, d_mu, count, static_cast<float>(mu_coef * mu_coef), d_stats);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_loss_grad_seeds(const float* d_pred, const float* d_sx, const float* d_psx, const float* d_mu, int64_t count,
+                         double mu_coef, const double* d_stats, float* d_g_pred, float* d_g_sx, float* d_g_psx,
+                         float* d_loss_out, void* stream) {
+  if (!d_pred || !d_sx || !d_psx || !d_mu || !d_stats) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_loss_grad_seeds: null pointer");
+  if (count <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_loss_grad_seeds: count <= 0");
+  loss_seeds_kernel<<<grid_for(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_pred, d_sx, d_psx, d_mu, count, static_cast<float>(mu_coef * mu_coef), d_stats, d_g_pred, d_g_sx, d_g_psx, d_loss_out);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+"""TEST INFRASTRUCTURE — makes the read-only reference (/root/reference) importable in the build
+container so the oracle can be pinned against it and golden vectors generated.
+
+The reference imports `optuna` and `bottleneck` at module top (train_SDRM.py:12, utilities.py:3);
+neither is installed here, so two tiny stubs are put in sys.modules.  `pandas` must be imported
+BEFORE the bottleneck stub (pandas probes sys.modules['bottleneck'] for a version).
+On a CPU-only box VAE.get_l2_reg calls .cuda() unconditionally (train_SDRM.py:262-263); that is
+patched to identity.  Nothing here is used by the product path, and nothing under tests -m gpu /
+bench.py / smoke() may call it (the reference does not exist on the GPU box).
+"""
+import os
+import sys
+import types
+
+REFERENCE_DIR = os.environ.get("SDRM_REFERENCE_DIR", "/root/reference")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_DIR, "train_SDRM.py"))
+
+
+def import_reference():
+    """Return the reference's train_SDRM module (imports utilities, dataloaders lazily)."""
+    if not reference_available():
+        raise RuntimeError(f"reference not found at {REFERENCE_DIR}")
+    import numpy as np
+    import pandas  # noqa: F401  (must precede the bottleneck stub)
+    import torch
+
+    if "optuna" not in sys.modules:
+        optuna = types.ModuleType("optuna")
+
+        class TrialPruned(Exception):
+            pass
+
+        optuna.TrialPruned = TrialPruned
+        optuna.exceptions = types.SimpleNamespace(TrialPruned=TrialPruned)
+        sys.modules["optuna"] = optuna
+    if "bottleneck" not in sys.modules:
+        bn = types.ModuleType("bottleneck")
+        bn.argpartition = lambda a, kth, axis=-1: np.argpartition(a, kth, axis=axis)
+        bn.__version__ = "1.3.7"
+        sys.modules["bottleneck"] = bn
+    if not torch.cuda.is_available():
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    if REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, REFERENCE_DIR)
+    import train_SDRM as ref  # noqa: E402
+
+    return ref

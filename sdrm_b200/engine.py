@@ -1,0 +1,122 @@
+"""Python owner of one sdrm_handle: packs the denoiser / decoder weights into the CUDA library and runs
+the persistent reverse-diffusion kernel.  All tensors are torch-owned; the handle only keeps its packed
+copies (include/sdrm_b200.h).  No CPU path: a CPU tensor or a missing library raises.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.detach().to(torch.float32).contiguous()
+    return t.detach()
+
+
+class SamplerEngine:
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.SdrmError("SDRM sampling needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        h = C.c_void_p()
+        _lib.check(self.lib.sdrm_create(C.byref(h), self.device.index or 0), "sdrm_create")
+        self.handle = h
+        self._den_key = None
+        self._dec_key = None
+        self._ws = None
+        self.T = self.L = self.I = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.sdrm_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---------------------------------------------------------------------------------------------
+    @staticmethod
+    def _key(tensors, extra):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if t is not None) + tuple(extra)
+
+    def pack_denoiser(self, diff_net, schedule, noise_divider, force=False):
+        """diff_net: sdrm_b200.models.SDRM (or any module with the same layer_tensors()); schedule = (b_t,a_t,ab_t)."""
+        lt = diff_net.layer_tensors()
+        T = diff_net.EMB_DIM
+        D, in_dim = lt["W0"].shape
+        L = in_dim - T
+        nh = diff_net.n_hidden_layers
+        sched = torch.cat([s.detach().to(self.device, torch.float32).reshape(-1) for s in schedule]).contiguous()
+        if sched.numel() != 3 * (T + 1):
+            raise ValueError(f"schedule must have 3*(T+1)={3 * (T + 1)} entries, got {sched.numel()}")
+        key = self._key(list(lt.values()), (float(noise_divider), T, L, D, nh, tuple(sched.tolist())))
+        if not force and key == self._den_key:
+            return
+        ts = {k: (_f32c(v.to(self.device)) if v is not None else None) for k, v in lt.items()}
+        st = _lib.stream_ptr()
+        rc = self.lib.sdrm_denoiser_pack(
+            self.handle, _lib.ptr(ts["We"]), _lib.ptr(ts["be"]), _lib.ptr(ts["W0"]), _lib.ptr(ts["b0"]),
+            _lib.ptr(ts["a0"]), _lib.ptr(ts["Wh"]), _lib.ptr(ts["bh"]), _lib.ptr(ts["ah"]), _lib.ptr(ts["Wo"]),
+            _lib.ptr(ts["bo"]), _lib.ptr(sched), T, L, D, nh, float(noise_divider), st)
+        _lib.check(rc, "sdrm_denoiser_pack")
+        self._keepalive_den = (ts, sched)
+        self._den_key = key
+        self.T, self.L = T, L
+
+    def pack_decoder(self, vae_net, force=False):
+        W1, b1 = vae_net.decoder[0].weight, vae_net.decoder[0].bias
+        W2, b2 = vae_net.decoder[2].weight, vae_net.decoder[2].bias
+        H, L = W1.shape
+        I = W2.shape[0]
+        key = self._key([W1, b1, W2, b2], (L, H, I))
+        if not force and key == self._dec_key:
+            return
+        ts = [_f32c(t.to(self.device)) for t in (W1, b1, W2, b2)]
+        rc = self.lib.sdrm_decoder_pack(self.handle, *[_lib.ptr(t) for t in ts], L, H, I, _lib.stream_ptr())
+        _lib.check(rc, "sdrm_decoder_pack")
+        self._keepalive_dec = ts
+        self._dec_key = key
+        self.I = I
+
+    # ---------------------------------------------------------------------------------------------
+    def workspace(self, n):
+        need = self.lib.sdrm_sample_workspace_bytes(self.handle, n)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws, need
+
+    def sample(self, n, row_offset=0, t_start=None, seed=0, out=None, latent_out=None, inj_xT=None, inj_z=None,
+               inj_keep=None, check=False):
+        """Run the chain + decode for n rows; returns logits [n, I] fp32 on the device."""
+        if self._den_key is None or self._dec_key is None:
+            raise _lib.SdrmError("pack_denoiser / pack_decoder must be called before sample")
+        if out is None:
+            out = torch.empty((n, self.I), dtype=torch.float32, device=self.device)
+        if out.dtype != torch.float32 or out.stride(1) != 1 or out.shape[0] < n or out.shape[1] < self.I:
+            raise ValueError("out must be float32 [>=n, >=I] with unit column stride")
+        if n == 0:
+            return out
+        ws, need = self.workspace(n)
+        if t_start is not None:
+            t_start = t_start.to(self.device, torch.int32).contiguous()
+            if t_start.numel() != n:
+                raise ValueError("t_start must have n entries")
+        for name, t, dt in (("inj_xT", inj_xT, torch.float32), ("inj_z", inj_z, torch.float32),
+                            ("inj_keep", inj_keep, torch.uint8)):
+            if t is not None and (t.dtype != dt or not t.is_contiguous() or t.device != self.device):
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
+        rc = self.lib.sdrm_sample(self.handle, n, row_offset, _lib.ptr(t_start), seed & (2 ** 64 - 1),
+                                  _lib.ptr(latent_out), _lib.ptr(out), out.stride(0), _lib.ptr(inj_xT),
+                                  _lib.ptr(inj_z), _lib.ptr(inj_keep), _lib.ptr(ws), need, _lib.stream_ptr())
+        _lib.check(rc, "sdrm_sample")
+        if check:
+            _lib.check(self.lib.sdrm_check_device_error(self.handle, _lib.stream_ptr()), "sdrm_sample (device)")
+        return out
+
+    def launch_count(self):
+        return int(self.lib.sdrm_last_launch_count(self.handle))

@@ -1,0 +1,106 @@
+"""GPU parity of K1 (sdrm_sample through the C ABI) against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import SAMPLER_GOLDENS, load_golden
+from helpers import max_scaled_err, modules_from_golden, random_modules, rel_fro, state_dicts
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # north_star: synthetic rows within 1e-3 relative (bf16 operands, fp32 accumulate)
+
+
+def _engine(diff, vae, T, nd):
+    from sdrm_b200.engine import SamplerEngine
+    from sdrm_b200.models import make_schedule
+    eng = SamplerEngine()
+    eng.pack_denoiser(diff, make_schedule(T, device="cuda"), nd)
+    eng.pack_decoder(vae)
+    return eng
+
+
+@pytest.mark.parametrize("name", SAMPLER_GOLDENS)
+@pytest.mark.parametrize("mode", ["full", "random"])
+def test_golden_injected_noise(name, mode):
+    """Same weights + same noise tensors the REFERENCE consumed -> rows match the reference output."""
+    g = load_golden(name)
+    diff, vae = modules_from_golden(g, "cuda")
+    eng = _engine(diff, vae, g["T"], g["nd"])
+    c = g[mode]
+    n = g["n"]
+    lat = torch.empty(n, g["L"], device="cuda")
+    t_start = c.get("t_start")
+    out = eng.sample(n, t_start=t_start.cuda() if t_start is not None else None, latent_out=lat,
+                     inj_xT=c["xT"].cuda().contiguous(), inj_z=c["z"].cuda().contiguous(),
+                     inj_keep=c["keep"].cuda().contiguous(), check=True)
+    ref = c["logits_ref"]
+    assert torch.isfinite(out).all()
+    assert rel_fro(out.cpu(), ref) < TOL, (rel_fro(out.cpu(), ref))
+    assert max_scaled_err(out.cpu(), ref) < 2 * TOL
+
+
+@pytest.mark.parametrize("shape", [
+    # n, I, H, L, T, nh, nd   (dataset-shaped, shortened chains so the CPU oracle stays fast)
+    (843, 1008, 930, 830, 12, 2, 1.0),    # cfg 1 ml-100k
+    (700, 3125, 490, 340, 10, 1, 1.0),    # cfg 2 ml-1m
+    (1200, 8582, 40, 40, 16, 5, 1.0),     # cfg 3 adm
+    (1208, 729, 550, 400, 43, 0, 0.2),    # cfg 4 alb, full T
+    (300, 2000, 1000, 950, 6, 4, 1.0),    # cfg 5 layer shapes (I shortened)
+])
+def test_vs_oracle_philox_noise(shape):
+    """In-kernel Philox noise: the oracle is fed the numpy restatement of the same streams."""
+    from oracle import philox_ref
+    from oracle import sdrm_oracle as orc
+    n, I, H, L, T, nh, nd = shape
+    diff, vae = random_modules(I, H, L, T, nh, seed=3, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    seed, row_offset = 0x1234ABCD5678, 1000
+    lat = torch.empty(n, L, device="cuda")
+    out = eng.sample(n, row_offset=row_offset, seed=seed, latent_out=lat, check=True).cpu()
+    xT, z, keep = philox_ref.sampler_noise(seed, row_offset, n, L, T)
+    dsd, vsd = state_dicts(diff, vae)
+    ref, ref_lat = orc.sample_full(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep),
+                                   return_latent=True)
+    emu = orc.sample_bf16_emulated(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep))
+    e_lat, e_out, e_emu = rel_fro(lat.cpu(), ref_lat), rel_fro(out, ref), rel_fro(out, emu)
+    print(f"shape={shape} latent rel {e_lat:.2e} logits rel {e_out:.2e} vs bf16-emulation {e_emu:.2e} "
+          f"max scaled {max_scaled_err(out, ref):.2e}")
+    assert e_out < TOL and e_lat < TOL
+    assert max_scaled_err(out, ref) < 2 * TOL
+    assert e_emu < 2e-4  # same rounding points -> much tighter: isolates kernel bugs from bf16 effects
+
+
+def test_partition_invariance():
+    """Rows depend only on (seed, global row id): any sharding / tile placement gives identical bits."""
+    n, I, H, L, T, nh, nd = 700, 300, 64, 72, 9, 1, 1.0
+    diff, vae = random_modules(I, H, L, T, nh, seed=5, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    whole = eng.sample(n, row_offset=0, seed=99, check=True).clone()
+    a = eng.sample(389, row_offset=0, seed=99, check=True).clone()
+    b = eng.sample(n - 389, row_offset=389, seed=99, check=True).clone()
+    assert torch.equal(whole, torch.cat([a, b]))
+
+
+def test_random_mode_matches_oracle():
+    from oracle import philox_ref
+    from oracle import sdrm_oracle as orc
+    n, I, H, L, T, nh, nd = 500, 256, 96, 88, 21, 2, 0.7
+    diff, vae = random_modules(I, H, L, T, nh, seed=8, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    rng = np.random.RandomState(4)
+    t_start = torch.from_numpy(rng.randint(1, T, size=n).astype(np.int32))
+    out = eng.sample(n, t_start=t_start.cuda(), seed=321, check=True).cpu()
+    xT, z, keep = philox_ref.sampler_noise(321, 0, n, L, T)
+    dsd, vsd = state_dicts(diff, vae)
+    ref = orc.sample_random(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep), t_start)
+    assert rel_fro(out, ref) < TOL
+
+
+def test_empty_and_ragged():
+    n, I, H, L, T, nh, nd = 1, 17, 8, 5, 3, 0, 1.0   # one row, ragged dims far from multiples of 16
+    diff, vae = random_modules(I, H, L, T, nh, seed=1, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    out = eng.sample(n, seed=1, check=True)
+    assert out.shape == (1, I) and torch.isfinite(out).all()
+    assert eng.sample(0).shape == (0, I)

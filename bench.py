@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Headline benchmark: synthetic users / second through the FULL T-step reverse chain + VAE decode.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl ours|reference]
+
+A "step" is one sample_ddpm-equivalent pass over one batch of users.  Default workload is the
+configuration BASELINE.json quotes its target on: the synthetic scale-up (T=178, VAE 1000/950, 4 hidden layers,
+20 000 items), 1 M users over 8 GPUs = 125 000 users per GPU, weak scaling (per-GPU work fixed).
+`value`   : device-timed, output stays in HBM.
+`e2e`     : through the public API with the rows delivered into pinned HOST memory (D2H inside the timed region).
+`roofline`: tensor-pipe fraction of the persistent kernel vs the measured sustained bf16 peak.
+`cpu_baseline`: the oracle (CPU restatement of the reference, incl. its RNG draws) on the box's host cores.
+`--impl reference` times that CPU implementation alone with all host threads (rank 0 only).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n per GPU, items, vae hidden, latent, T, hidden layers, noise divider
+    "cfg1": dict(n=843, I=1008, H=930, L=830, T=83, nh=2, nd=1.0, desc="ml-100k SVD augment"),
+    "cfg2": dict(n=5429, I=3125, H=490, L=340, T=78, nh=1, nd=1.0, desc="ml-1m MLP augment"),
+    "cfg3": dict(n=9558, I=8582, H=40, L=40, T=93, nh=5, nd=1.0, desc="ADM NeuMF augment"),
+    "cfg4": dict(n=1208, I=729, H=550, L=400, T=43, nh=0, nd=0.2, desc="ALB MLP augment"),
+    "cfg5": dict(n=125000, I=20000, H=1000, L=950, T=178, nh=4, nd=1.0,
+                 desc="synthetic scale-up 1M users x 20k items over 8 GPUs (125k users/GPU)"),
+}
+
+
+def flops_per_user(w):
+    """Algorithmic FLOPs: T*2*L^2*(2+nh) + 2*(L*H + H*I); time embedding hoisted, bf16x3 credited once."""
+    return w["T"] * 2 * w["L"] ** 2 * (2 + w["nh"]) + 2 * (w["L"] * w["H"] + w["H"] * w["I"])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(tflops=p.get("bf16_tflops_sustained", 1413.8), hbm=p.get("hbm_gbs", 6535.7), source="measured")
+    return dict(tflops=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_models(w, device, seed=0):
+    import torch
+    from sdrm_b200.models import SDRM, VAE
+    torch.manual_seed(seed)  # reference initialisers; timing is weight-independent (random-init, synthetic data)
+    vae = VAE(input_dim=w["I"], hidden_dim=w["H"], latent_dim=w["L"]).to(device).eval()
+    diff = SDRM(N_ITEMS=w["L"], EMB_DIM=w["T"], LATENT_DIM=w["L"], n_hidden_layers=w["nh"]).to(device).eval()
+    return diff, vae
+
+
+def cpu_reference_rate(w, rows, threads, repeats=1):
+    """users/s of the CPU restatement of sample_ddpm (oracle), RNG draws inside the timed region like the reference."""
+    import torch
+    from oracle import sdrm_oracle as orc
+    torch.set_num_threads(threads)
+    diff, vae = build_models(w, "cpu")
+    dsd = {k: v.detach() for k, v in diff.state_dict().items()}
+    vsd = {k: v.detach() for k, v in vae.state_dict().items()}
+    T, L = w["T"], w["L"]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            sched = orc.make_schedule(T)
+            x = torch.randn(rows, L)
+            for i in range(T, 0, -1):
+                z = torch.randn_like(x) * w["nd"] if i > 1 else 0
+                keep = torch.empty_like(x).bernoulli_(0.5)
+                eps = orc.denoiser_forward(dsd, x, torch.full((rows,), i, dtype=torch.long), keep)
+                x = orc.posterior_step(x, eps, z, i, sched)
+            out = orc.vae_decode(vsd, x)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    assert out.shape == (rows, w["I"])
+    return rows / best, best
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rows = args.cpu_rows or max(64, min(2048, int(2.0e11 / flops_per_user(w))))
+    for _ in range(args.warmup):
+        cpu_reference_rate(w, max(8, rows // 8), threads)
+    t_all = 0.0
+    for _ in range(args.steps):
+        rate, dt = cpu_reference_rate(w, rows, threads)
+        t_all += dt
+    value = rows * args.steps / t_all
+    line = {
+        "impl": "reference", "metric": "synthetic users/sec (full reverse diffusion + decode)", "value": value,
+        "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (random-init weights of the named shape, torch CPU RNG)",
+        "config": {"workload": args.workload, **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
+                   "rows_per_step": rows, "note": "bounded sample of the workload on host cores"},
+        "cpu_baseline": {"value": value, "unit": "users/s", "cores": threads, "kind": "port",
+                         "sample": f"{rows} users x full T={w['T']} chain + decode per step, oracle/sdrm_oracle.py"},
+        "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sdrm_b200.train_SDRM import engine_for, sample_ddpm, sample_ddpm_host
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.rows or w["n"]
+    diff, vae = build_models(w, dev)
+    row_offset = rank * n
+    out = torch.empty((n, w["I"]), dtype=torch.float32, device=dev)
+
+    def step(seed):
+        sample_ddpm(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=seed, row_offset=row_offset, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(1000 + i)
+    eng = engine_for(diff, dev)
+    barrier()
+    from sdrm_b200 import _lib
+    _lib.check(eng.lib.sdrm_check_device_error(eng.handle, _lib.stream_ptr()), "warmup")
+    launches_per_step = eng.launch_count()
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step(2000 + i)
+        ev[i + 1].record()
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end: rows land in pinned host memory (what main.py's .cpu().numpy() consumes)
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n, w["I"]), dtype=torch.float32, pin_memory=True)
+        sample_ddpm_host(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=5, row_offset=row_offset, host_out=host)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.e2e_steps):
+            sample_ddpm_host(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=3000 + i, row_offset=row_offset,
+                             host_out=host)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * n * args.e2e_steps / float(dt.item()), "unit": "users/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": n * w["I"] * 4, "steps": args.e2e_steps,
+               "note": "sample_ddpm_host: chunked chain+decode with the D2H of chunk c overlapping chunk c+1"}
+        del host
+
+    if rank == 0:
+        peaks = measured_peaks()
+        F = flops_per_user(w)
+        kernel_ms = statistics.mean(step_ms)  # one persistent kernel per step
+        achieved = F * n / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + " sustained bf16",
+                    "kernel": "sdrm_layer_engine_kernel", "kernel_ms": kernel_ms, "flops_per_user": F,
+                    "hbm_min_bytes_per_user": 4 * w["I"],
+                    "hbm_frac_of_logits_write": (4 * w["I"] * n / (kernel_ms * 1e-3) / 1e9) / peaks["hbm"]}
+        cpu = None
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            rows = args.cpu_rows or max(64, min(1024, int(1.0e11 / F)))
+            rate, dt = cpu_reference_rate(w, rows, threads)
+            cpu = {"value": rate, "unit": "users/s", "cores": threads, "kind": "port",
+                   "sample": f"{rows} users x full T={w['T']} chain + decode, {dt:.1f} s, oracle/sdrm_oracle.py incl. RNG draws"}
+        line = {
+            "metric": "synthetic users/sec (full reverse diffusion + decode)", "value": value, "unit": "users/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (random-init weights of the named shape, in-kernel Philox noise)",
+            "config": {"workload": args.workload, "desc": w["desc"], "users_per_gpu": n,
+                       **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
+                       "l2": "each step writes n*I*4 bytes of logits (>> 126 MB L2 for cfg5); no reuse across steps",
+                       "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
+            "clocks": clock_info, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg5")
+    ap.add_argument("--rows", type=int, default=None, help="override users per GPU")
+    ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+    if world != args.gpus and args.gpus > 1:
+        raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    run_ours(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

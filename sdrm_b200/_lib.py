@@ -20,13 +20,14 @@ SIGNATURES = {
     "sdrm_denoiser_pack": (C.c_int, [_P] + [_P] * 11 + [C.c_int] * 4 + [C.c_float, _P]),
     "sdrm_decoder_pack": (C.c_int, [_P] + [_P] * 4 + [C.c_int] * 3 + [_P]),
     "sdrm_sample_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
-    "sdrm_sample": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_uint64, _P, _P, C.c_int64, _P, _P, _P, _P,
+    "sdrm_sample": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, C.c_uint64, _P, _P, C.c_int64, _P, _P, _P, _P,
                               C.c_size_t, _P]),
     "sdrm_last_launch_count": (C.c_int, [_P]),
     "sdrm_check_device_error": (C.c_int, [_P, _P]),
     "sdrm_probe_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "sdrm_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),
+    "sdrm_topk_f64": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),
     "sdrm_recall_ndcg_at_k": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int64, C.c_int, C.c_int64, _P, _P, _P, _P]),
     "sdrm_noise_inputs": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, C.c_float, C.c_double, C.c_uint64, C.c_int64,
                                     _P, _P, _P, _P, _P, _P, _P, _P]),

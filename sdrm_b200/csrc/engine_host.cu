@@ -350,7 +350,8 @@ size_t sdrm_sample_workspace_bytes(const sdrm_handle* h, int64_t n) {
   return static_cast<size_t>(grid) * stride;
 }
 
-int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_t_start, uint64_t seed,
+int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_t_start, const int32_t* d_row_ids,
+                uint64_t seed,
                 float* d_x0_out, float* d_logits, int64_t ld_logits, const float* d_inj_xT, const float* d_inj_z,
                 const uint8_t* d_inj_mask, void* d_workspace, size_t workspace_bytes, void* stream) {
   if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: null handle");
@@ -389,6 +390,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.n_rows = n; P.row_offset = row_offset;
   P.coef = h->coef;
   P.t_start = d_t_start;
+  P.row_ids = d_row_ids;
   P.x0_out = d_x0_out;
   P.logits = d_logits; P.ld_logits = ld_logits;
   P.inj_xT = d_inj_xT; P.inj_z = d_inj_z; P.inj_mask = d_inj_mask;

@@ -211,11 +211,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       uint8_t* sc = scratch_of(tile);
       float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
-      const long long row = tile * TILE_M + r;
-      const bool valid = row < P.n_rows;
+      const long long prow = tile * TILE_M + r;   // physical row of this launch
+      const bool valid = prow < P.n_rows;
+      const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
       const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
       int t_row = P.T;
-      if (P.t_start) t_row = valid ? P.t_start[row] : 0;
+      if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
 
       // ---- tile start step = max over rows
       int m = t_row;

@@ -46,7 +46,8 @@ struct ChainParams {
   int preloaded_input;    // probe mode: activation images were packed per TILE by the host
   long long n_rows, row_offset;
   const float* coef;      // [T+1][4] = c1, c2, sigma*nd, 0   (denoise_add_noise, train_SDRM.py:20-25)
-  const int32_t* t_start; // per-row start step or nullptr
+  const int32_t* t_start; // per-row start step or nullptr (indexed by physical row)
+  const int32_t* row_ids; // physical -> logical row or nullptr
   float* x0_out;          // [n, L] or nullptr
   float* logits;          // [n, ld_logits]
   long long ld_logits;

@@ -16,33 +16,36 @@
 
 namespace sdrm {
 
-__device__ __forceinline__ bool before(float av, int ai, float bv, int bi) {
+template <typename T>
+__device__ __forceinline__ bool before(T av, int ai, T bv, int bi) {
   // true when (av, ai) ranks strictly ahead of (bv, bi)
   return (av > bv) || (av == bv && ai < bi);
 }
 
-__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ scores, long long rows, int n_items,
+template <typename T>
+__global__ void __launch_bounds__(256) topk_rows_kernel(const T* __restrict__ scores, long long rows, int n_items,
                                                         long long ld, int k, int* __restrict__ idx_out,
-                                                        float* __restrict__ val_out) {
+                                                        T* __restrict__ val_out) {
+  const T NEG_INF = static_cast<T>(-CUDART_INF_F);
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* x = scores + row * ld;
+  const T* x = scores + row * ld;
 
-  float v0 = -CUDART_INF_F, v1 = -CUDART_INF_F;  // entries lane and lane+32
+  T v0 = NEG_INF, v1 = NEG_INF;  // entries lane and lane+32
   int i0 = INT_MAX, i1 = INT_MAX;
   const int kth_lane = (k - 1) & 31;
   const bool kth_hi = (k - 1) >= 32;
-  float thr_v = -CUDART_INF_F;
+  T thr_v = NEG_INF;
   int thr_i = INT_MAX;
 
   for (int base = 0; base < n_items; base += 128) {
-    float c[4];
+    T c[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int j = base + u * 32 + lane;
-      float v = (j < n_items) ? __ldg(x + j) : -CUDART_INF_F;
-      c[u] = (v != v) ? -CUDART_INF_F : v;  // NaN -> -inf
+      T v = (j < n_items) ? __ldg(x + j) : NEG_INF;
+      c[u] = (v != v) ? NEG_INF : v;  // NaN -> -inf
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -52,16 +55,16 @@ __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict_
       while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        const float cv = __shfl_sync(0xffffffffu, c[u], src);
+        const T cv = __shfl_sync(0xffffffffu, c[u], src);
         const int ci = base + u * 32 + src;
         if (!before(cv, ci, thr_v, thr_i)) continue;  // threshold moved since the ballot
         const int pos = __popc(__ballot_sync(0xffffffffu, before(v0, i0, cv, ci))) +
                         __popc(__ballot_sync(0xffffffffu, before(v1, i1, cv, ci)));
-        const float up_v0 = __shfl_up_sync(0xffffffffu, v0, 1);
+        const T up_v0 = __shfl_up_sync(0xffffffffu, v0, 1);
         const int up_i0 = __shfl_up_sync(0xffffffffu, i0, 1);
-        float up_v1 = __shfl_up_sync(0xffffffffu, v1, 1);
+        T up_v1 = __shfl_up_sync(0xffffffffu, v1, 1);
         int up_i1 = __shfl_up_sync(0xffffffffu, i1, 1);
-        const float wrap_v = __shfl_sync(0xffffffffu, v0, 31);
+        const T wrap_v = __shfl_sync(0xffffffffu, v0, 31);
         const int wrap_i = __shfl_sync(0xffffffffu, i0, 31);
         if (lane == 0) { up_v1 = wrap_v; up_i1 = wrap_i; }
         if (lane == pos) { v0 = cv; i0 = ci; }
@@ -116,20 +119,31 @@ __global__ void __launch_bounds__(256) recall_ndcg_kernel(const int* __restrict_
 
 using namespace sdrm;
 
-extern "C" {
-
-int sdrm_topk(const float* d_scores, int64_t rows, int n_items, int64_t ld, int k, int32_t* d_idx_out,
-              float* d_val_out, void* stream) {
+template <typename T>
+static int topk_impl(const T* d_scores, int64_t rows, int n_items, int64_t ld, int k, int32_t* d_idx_out, T* d_val_out,
+                     void* stream) {
   if (!d_scores || !d_idx_out) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_topk: null pointer");
   if (k < 1 || k > 64) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_topk: k must be in [1, 64]");
   if (n_items < 1 || ld < n_items) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_topk: bad shape");
   if (rows <= 0) return SDRM_OK;
   const int warps = 8;
   const long long blocks = (rows + warps - 1) / warps;
-  topk_rows_kernel<<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+  topk_rows_kernel<T><<<static_cast<unsigned>(blocks), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       d_scores, rows, n_items, ld, k, d_idx_out, d_val_out);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
+}
+
+extern "C" {
+
+int sdrm_topk(const float* d_scores, int64_t rows, int n_items, int64_t ld, int k, int32_t* d_idx_out,
+              float* d_val_out, void* stream) {
+  return topk_impl<float>(d_scores, rows, n_items, ld, k, d_idx_out, d_val_out, stream);
+}
+
+int sdrm_topk_f64(const double* d_scores, int64_t rows, int n_items, int64_t ld, int k, int32_t* d_idx_out,
+                  double* d_val_out, void* stream) {
+  return topk_impl<double>(d_scores, rows, n_items, ld, k, d_idx_out, d_val_out, stream);
 }
 
 int sdrm_recall_ndcg_at_k(const int32_t* d_topk_idx, int k_stored, int k, const float* d_heldout, int64_t rows,

@@ -90,7 +90,7 @@ class SamplerEngine:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._ws, need
 
-    def sample(self, n, row_offset=0, t_start=None, seed=0, out=None, latent_out=None, inj_xT=None, inj_z=None,
+    def sample(self, n, row_offset=0, t_start=None, row_ids=None, seed=0, out=None, latent_out=None, inj_xT=None, inj_z=None,
                inj_keep=None, check=False):
         """Run the chain + decode for n rows; returns logits [n, I] fp32 on the device."""
         if self._den_key is None or self._dec_key is None:
@@ -106,11 +106,15 @@ class SamplerEngine:
             t_start = t_start.to(self.device, torch.int32).contiguous()
             if t_start.numel() != n:
                 raise ValueError("t_start must have n entries")
+        if row_ids is not None:
+            row_ids = row_ids.to(self.device, torch.int32).contiguous()
+            if row_ids.numel() != n:
+                raise ValueError("row_ids must have n entries")
         for name, t, dt in (("inj_xT", inj_xT, torch.float32), ("inj_z", inj_z, torch.float32),
                             ("inj_keep", inj_keep, torch.uint8)):
             if t is not None and (t.dtype != dt or not t.is_contiguous() or t.device != self.device):
                 raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
-        rc = self.lib.sdrm_sample(self.handle, n, row_offset, _lib.ptr(t_start), seed & (2 ** 64 - 1),
+        rc = self.lib.sdrm_sample(self.handle, n, row_offset, _lib.ptr(t_start), _lib.ptr(row_ids), seed & (2 ** 64 - 1),
                                   _lib.ptr(latent_out), _lib.ptr(out), out.stride(0), _lib.ptr(inj_xT),
                                   _lib.ptr(inj_z), _lib.ptr(inj_keep), _lib.ptr(ws), need, _lib.stream_ptr())
         _lib.check(rc, "sdrm_sample")

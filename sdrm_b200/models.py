@@ -61,11 +61,14 @@ class SDRM(nn.Module):
             emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
         return emb
 
-    def forward(self, x, t, keep_mask=None):
+    def forward(self, x, t, keep_mask=None, prescaled=False):
         """eps_theta(x, t).  Dropout(p=.5) is ALWAYS active like the reference (F.dropout default
-        training=True, train_SDRM.py:100); pass keep_mask to make it deterministic."""
+        training=True, train_SDRM.py:100); pass keep_mask to make it deterministic, or prescaled=True when
+        x already is input * keep * 2 (the fused noising kernel produces it that way)."""
         emb = self.emb_layer(self.timestep_embedding(t, self.EMB_DIM))
-        if keep_mask is None:
+        if prescaled:
+            pass
+        elif keep_mask is None:
             x = F.dropout(x, p=0.5)
         else:
             x = x * keep_mask.to(x.dtype) * 2.0

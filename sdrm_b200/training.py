@@ -1,0 +1,103 @@
+"""The diffusion training step (reference: train_SDRM.py:321-337 + score_matching_loss 191-199).
+
+Per minibatch of latents mu = VAE.encode(x):
+  1. K2 `sdrm_noise_inputs`  : noise, x_t = sqrt(ab_t) mu + (1-ab_t) noise, x_p = mu + .1 noise and the three
+                               dropout-scaled denoiser inputs, one fused pass (in-kernel Philox);
+  2. the three denoiser forwards run as ONE [3B, L] batch through the shared MLP (rows are independent, so
+     this is the same arithmetic; the dense layers are library GEMMs under autograd);
+  3. K2 `sdrm_loss_stats` + `sdrm_loss_grad_seeds`: five fp64 partial sums -> (optional all-reduce over the
+     data-parallel group: the loss divides by the GLOBAL-batch variance) -> scalar loss and
+     the closed-form gradient seeds, wrapped in a torch.autograd.Function.
+"""
+import torch
+
+from . import _lib
+
+
+class CudaLossBackend:
+    """Calls the C ABI.  Tests may substitute an object with the same three methods."""
+
+    def __init__(self):
+        self.lib = _lib.load()
+
+    def noise_inputs(self, mu, t, ab_t, nd, mu_coef, seed, row_offset, inj_noise=None, inj_masks=None, want_masks=False):
+        B, L = mu.shape
+        outs = [torch.empty_like(mu) for _ in range(4)]
+        masks = torch.empty((3, B, L), dtype=torch.uint8, device=mu.device) if want_masks else None
+        rc = self.lib.sdrm_noise_inputs(_lib.ptr(mu), _lib.ptr(t), _lib.ptr(ab_t), B, L, float(nd), float(mu_coef),
+                                        seed & (2 ** 64 - 1), int(row_offset), _lib.ptr(inj_noise), _lib.ptr(inj_masks),
+                                        _lib.ptr(outs[0]), _lib.ptr(outs[1]), _lib.ptr(outs[2]), _lib.ptr(outs[3]),
+                                        _lib.ptr(masks), _lib.stream_ptr())
+        _lib.check(rc, "sdrm_noise_inputs")
+        return outs[0], outs[1], outs[2], outs[3], masks
+
+    def stats(self, pred, sx, psx, mu, mu_coef):
+        st = torch.zeros(5, dtype=torch.float64, device=pred.device)
+        rc = self.lib.sdrm_loss_stats(_lib.ptr(pred), _lib.ptr(sx), _lib.ptr(psx), _lib.ptr(mu), pred.numel(),
+                                      float(mu_coef), _lib.ptr(st), _lib.stream_ptr())
+        _lib.check(rc, "sdrm_loss_stats")
+        return st
+
+    def seeds(self, pred, sx, psx, mu, mu_coef, stats):
+        g = [torch.empty_like(pred) for _ in range(3)]
+        loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+        rc = self.lib.sdrm_loss_grad_seeds(_lib.ptr(pred), _lib.ptr(sx), _lib.ptr(psx), _lib.ptr(mu), pred.numel(),
+                                           float(mu_coef), _lib.ptr(stats), _lib.ptr(g[0]), _lib.ptr(g[1]), _lib.ptr(g[2]),
+                                           _lib.ptr(loss), _lib.stream_ptr())
+        _lib.check(rc, "sdrm_loss_grad_seeds")
+        return g[0], g[1], g[2], loss
+
+
+class ScoreMatchingLoss(torch.autograd.Function):
+    """loss = 0.5 (mean((sd-r)^2) + mean((r-sx)^2)) / (1e-8 + var(r)),  r = pred - mu, sd = (psx - sx)/mu_coef^2,
+    with means / variance over the GLOBAL batch when `group` is a process group."""
+
+    @staticmethod
+    def forward(ctx, pred, sx, psx, mu, mu_coef, backend, group):
+        pred, sx, psx, mu = (v.contiguous() for v in (pred, sx, psx, mu))
+        stats = backend.stats(pred, sx, psx, mu, mu_coef)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+        g_pred, g_sx, g_psx, loss = backend.seeds(pred, sx, psx, mu, mu_coef, stats)
+        ctx.save_for_backward(g_pred, g_sx, g_psx)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        g_pred, g_sx, g_psx = ctx.saved_tensors
+        return grad_out * g_pred, grad_out * g_sx, grad_out * g_psx, None, None, None, None
+
+
+class DiffusionTrainStep:
+    """Builds the loss of one minibatch; the caller does zero_grad / backward / optimizer.step like the reference."""
+
+    def __init__(self, diff_net, ab_t, timesteps, noise_divider, mu_coef=0.1, group=None, backend=None, seed=None):
+        self.net = diff_net
+        self.ab_t = ab_t.detach().to(torch.float32).contiguous()
+        self.T = int(timesteps)
+        self.nd = float(noise_divider)
+        self.mu_coef = mu_coef
+        self.group = group
+        self.backend = backend if backend is not None else CudaLossBackend()
+        self.base_seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if seed is None else int(seed)
+        self.step_index = 0
+        self.row_offset = 0  # data-parallel ranks set this to their first global row of the minibatch
+
+    def loss(self, mu, t=None, inj_noise=None, inj_masks=None):
+        if isinstance(self.backend, CudaLossBackend) and mu.device.type != "cuda":
+            raise _lib.SdrmError("the SDRM training step needs CUDA tensors (no CPU fallback)")
+        mu = mu.detach().to(torch.float32).contiguous()
+        B = mu.shape[0]
+        if t is None:
+            # CPU generator then .to(device), like the reference (train_SDRM.py:327)
+            t = torch.randint(1, self.T + 1, (B,)).to(mu.device)
+        t = t.to(mu.device, torch.int64).contiguous()
+        seed = self.base_seed + self.step_index
+        self.step_index += 1
+        _, in_pert, in_clean, in_shift, _ = self.backend.noise_inputs(
+            mu, t, self.ab_t.to(mu.device), self.nd, self.mu_coef, seed, self.row_offset, inj_noise, inj_masks)
+        x3 = torch.cat([in_pert, in_clean, in_shift], dim=0)
+        out3 = self.net(x3, t.repeat(3), prescaled=True)
+        pred, sx, psx = out3[:B], out3[B:2 * B], out3[2 * B:]
+        return ScoreMatchingLoss.apply(pred, sx, psx, mu, self.mu_coef, self.backend, self.group)

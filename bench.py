@@ -132,7 +132,7 @@ def run_reference(args, w, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = args.cpu_rows or max(64, min(2048, int(2.0e11 / flops_per_user(w))))
+    rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / flops_per_user(w))))
     for _ in range(args.warmup):
         cpu_reference_rate(w, max(8, rows // 8), threads)
     t_all = 0.0
@@ -235,7 +235,7 @@ def run_ours(args, w, rank, world, local_rank):
         cpu = None
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            rows = args.cpu_rows or max(64, min(1024, int(1.0e11 / F)))
+            rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / F)))
             rate, dt = cpu_reference_rate(w, rows, threads)
             cpu = {"value": rate, "unit": "users/s", "cores": threads, "kind": "port",
                    "sample": f"{rows} users x full T={w['T']} chain + decode, {dt:.1f} s, oracle/sdrm_oracle.py incl. RNG draws"}

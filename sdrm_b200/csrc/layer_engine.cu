@@ -10,7 +10,8 @@
 //   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
 //     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the
 //     bf16 (or bf16 hi/lo) re-quantisation, and write the next layer's A images (L2-resident scratch);
-//   * warp 0 = TMA producer, warp 1 = UMMA issuer (one elected thread), warps 2-5 = epilogue.
+//   * warp 0 = TMA producer, warp 1 = UMMA issuer (one elected thread), warps 2-17 = epilogue; the epilogue
+//     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
 // Rows are independent, so there is no inter-CTA synchronisation anywhere.
 #include "layer_engine.cuh"
 #include "philox.cuh"
@@ -31,7 +32,7 @@ struct SmemLayout {
   uint32_t tile_ready;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // write 16 consecutive bf16 features [f0, f0+16) of tile row r into a k-block image buffer
 __device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8]) {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   uint8_t* misc = smem + NUM_STAGES * STAGE_BYTES + 8 * (2 * NUM_STAGES + 6);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
-  volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x 4 ints
+  volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,10 +90,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     }
     mbar_init(S.acc_full[0], 1);
     mbar_init(S.acc_full[1], 1);
-    mbar_init(S.acc_empty[0], 4);
-    mbar_init(S.acc_empty[1], 4);
-    mbar_init(S.act_ready, 4);
-    mbar_init(S.tile_ready, 4);
+    mbar_init(S.acc_empty[0], EPI_WARPS);
+    mbar_init(S.acc_empty[1], EPI_WARPS);
+    mbar_init(S.act_ready, EPI_WARPS);
+    mbar_init(S.tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -194,8 +195,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     }
   } else {
     // ======================================= epilogue warps =====================================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;            // tile row owned by this thread
+    // 16 warps: warp (q, sub) reads TMEM lane quarter q (rows 32q..32q+31) and owns the 16-column groups
+    // g = sub (mod 4).  One thread always touches the same (row, columns) of the fp32 state, so the state
+    // needs no synchronisation at all.
+    const int q = warp & 3;
+    const int sub = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t cc = 0;
     int it = 0;
@@ -204,9 +209,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     if (!P.preloaded_input) {
       uint4* z = reinterpret_cast<uint4*>(scratch_of(blockIdx.x));
       const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
-      for (size_t i = threadIdx.x - 64; i < n16; i += 128) z[i] = make_uint4(0, 0, 0, 0);
+      for (size_t i = threadIdx.x - 64; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       epi_bar_sync();
     }
+    // noise groups of this thread per step: g = sub, sub + 4, ... < Lg16
+    const int noise_total = (P.Lg16 > sub) ? (P.Lg16 - sub + EPI_SUB - 1) / EPI_SUB : 0;
+    int noise_slots_per_step = 0;
+    for (int l = 0; l + 1 < P.n_step; ++l) noise_slots_per_step += P.step[l].NCH;
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       uint8_t* sc = scratch_of(tile);
@@ -222,10 +231,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       int m = t_row;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) warp_max[(it & 1) * 4 + q] = m;
+      if (lane == 0) warp_max[(it & 1) * EPI_WARPS + (warp - 2)] = m;
       epi_bar_sync();
-      int T_tile = max(max(warp_max[(it & 1) * 4 + 0], warp_max[(it & 1) * 4 + 1]),
-                       max(warp_max[(it & 1) * 4 + 2], warp_max[(it & 1) * 4 + 3]));
+      int T_tile = 0;
+#pragma unroll
+      for (int w = 0; w < EPI_WARPS; ++w) T_tile = max(T_tile, warp_max[(it & 1) * EPI_WARPS + w]);
       if (P.n_step == 0) T_tile = 0;
 
       auto keep_mask16 = [&](int step, int g16) -> uint32_t {
@@ -244,10 +254,44 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         return philox_mask16(P.seed, STREAM_MASK, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16));
       };
 
-      // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38)
+      // Noise half of the posterior update, done AHEAD of the eps GEMM of the same step (z does not depend on the
+      // network): state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
+      auto noise_group = [&](int step, int g16) {
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
+        const bool active = valid && (step <= t_row);
+        if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
+        const float c2 = cf.y, sg = cf.z;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4* px = xstate_ptr(xs, g16, j, r);
+          const float4 xo = *px;
+          float z4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (sg != 0.0f) {
+            if (P.inj_z) {
+              const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int f = g16 * 16 + 4 * j + e;
+                z4[e] = f < P.L ? zp[f] : 0.0f;
+              }
+            } else {
+              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z4);
+            }
+          }
+          float4 o;
+          const int f = g16 * 16 + 4 * j;
+          o.x = (f + 0 < P.L) ? fmaf(sg, z4[0], xo.x * c2) : 0.0f;
+          o.y = (f + 1 < P.L) ? fmaf(sg, z4[1], xo.y * c2) : 0.0f;
+          o.z = (f + 2 < P.L) ? fmaf(sg, z4[2], xo.z * c2) : 0.0f;
+          o.w = (f + 3 < P.L) ? fmaf(sg, z4[3], xo.w * c2) : 0.0f;
+          *px = o;
+        }
+      };
+
+      // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38); also the noise half of the first step
       if (P.n_step > 0) {
         uint8_t* in0 = sc + static_cast<size_t>(P.step[0].in_hi) * P.act_buf_bytes;
-        for (int g = 0; g < P.Lg16; ++g) {
+        for (int g = sub; g < P.Lg16; g += EPI_SUB) {
           float x[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -277,43 +321,53 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             pk[e] = pack_bf16x2(a0, a1);
           }
           store_act16(in0, r, g * 16, pk);
+          noise_group(T_tile, g);
         }
       }
-      if (q == 0 && lane == 0) tile_T[it & 1] = T_tile;
+      if (warp == 2 && lane == 0) tile_T[it & 1] = T_tile;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(S.tile_ready);
 
+      int noise_done = noise_total;   // the tile's first step got its noise in the init above
+      int noise_slots = 0;
+
       // ---- layers
-      auto run = [&](const LayerDesc& ld, int step, bool last_of_tile) {
+      auto run = [&](const LayerDesc& ld, int step, int layer_idx, bool last_of_tile) {
         uint8_t* out_hi = sc + static_cast<size_t>(ld.out_hi) * P.act_buf_bytes;
         uint8_t* out_lo = sc + static_cast<size_t>(ld.out_lo) * P.act_buf_bytes;
         const float* bias_row = ld.bias + static_cast<size_t>(step) * ld.bias_step_stride;
         const float slope = ld.slope ? __ldg(ld.slope) : 0.0f;
-        float c1 = 0.f, c2 = 0.f, sg = 0.f;
+        float c12 = 0.f;
+        const bool active = valid && (step <= t_row);
         if (ld.kind == EPI_POSTERIOR) {
           const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
-          c1 = cf.x; c2 = cf.y; sg = cf.z;
+          c12 = active ? cf.x * cf.y : 0.0f;
+          while (noise_done < noise_total) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
+        } else if (step >= 1 && layer_idx == 0 && step != T_tile) {
+          noise_done = 0;
+          noise_slots = noise_slots_per_step;
         }
-        const bool active = step <= t_row;
+        const int ngroups = ld.NC >> 4;
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
           mbar_wait(S.acc_full[buf], (cc >> 1) & 1u, err, WD_EPI_ACC);
           tc_fence_after();
-          const int ngroups = ld.NC >> 4;
-          for (int g = 0; g < ngroups; ++g) {
+          for (int g = sub; g < ngroups; g += EPI_SUB) {
             uint32_t v[16];
             tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
-            tmem_ld_wait();
             const int f0 = c * ld.NC + g * 16;
+            float4 b4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias_row + f0) + j);
+            tmem_ld_wait();
             float h[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(bias_row + f0) + j);
-              h[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x;
-              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+              h[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4[j].x;
+              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
+              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
+              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
             }
             if (ld.kind == EPI_PRELU) {
               uint32_t pk[8];
@@ -325,37 +379,23 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               }
               store_act16(out_hi, r, f0, pk);
             } else if (ld.kind == EPI_POSTERIOR) {
-              // x_{i-1} = (x_i - eps * (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) * nd * z
+              // x_{i-1} = (x_i - eps (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) nd z; the state already holds
+              // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise_group), so only the eps term is left.
               const int g16 = f0 >> 4;
               if (g16 < P.Lg16) {
                 float xn[16];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float4 xo = *xstate_ptr(xs, g16, j, r);
-                  float z4[4] = {0.f, 0.f, 0.f, 0.f};
-                  if (sg != 0.0f && valid) {
-                    if (P.inj_z) {
-                      const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
-#pragma unroll
-                      for (int e = 0; e < 4; ++e) {
-                        const int f = f0 + 4 * j + e;
-                        z4[e] = f < P.L ? zp[f] : 0.0f;
-                      }
-                    } else {
-                      philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step),
-                                     static_cast<uint32_t>(g16 * 4 + j), z4);
-                    }
-                  }
-                  const float xv[4] = {xo.x, xo.y, xo.z, xo.w};
+                  float4* px = xstate_ptr(xs, g16, j, r);
+                  const float4 xb = *px;
+                  const float xv[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int f = f0 + 4 * j + e;
-                    const float eps = fast_tanh(h[4 * j + e]);
-                    float nv = (xv[e] - eps * c1) * c2 + sg * z4[e];
-                    nv = active ? nv : xv[e];
+                    const float nv = fmaf(-c12, fast_tanh(h[4 * j + e]), xv[e]);
                     xn[4 * j + e] = (valid && f < P.L) ? nv : 0.0f;
                   }
-                  *xstate_ptr(xs, g16, j, r) = make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]);
+                  *px = make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]);
                 }
                 if (step > 1) {
                   const uint32_t keep = keep_mask16(step - 1, g16);
@@ -416,6 +456,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           __syncwarp();
           if (lane == 0) mbar_arrive(S.acc_empty[buf]);
           ++cc;
+          // spare time while the tensor core works on the next chunk: a slice of this step's noise
+          if (ld.kind == EPI_PRELU && noise_slots > 0) {
+            const int todo = (noise_total - noise_done + noise_slots - 1) / noise_slots;
+            for (int k = 0; k < todo; ++k) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
+            --noise_slots;
+          }
         }
         if (!last_of_tile) {
           fence_proxy_async();
@@ -424,8 +470,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         }
       };
       for (int i = T_tile; i >= 1; --i)
-        for (int l = 0; l < P.n_step; ++l) run(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1));
-      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l == P.n_dec - 1);
+        for (int l = 0; l < P.n_step; ++l) run(P.step[l], i, l, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1));
+      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l, l == P.n_dec - 1);
     }
   }
 

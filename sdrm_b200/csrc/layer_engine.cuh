@@ -14,8 +14,11 @@ constexpr int STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES_MAX;
 constexpr int NUM_STAGES = 4;
 constexpr int MAX_STEP_LAYERS = 8;                 // 2 + nh, nh <= 6
 constexpr int NUM_ACT_BUFS = 4;
-constexpr int ENGINE_THREADS = 192;                // warp0 TMA, warp1 UMMA, warps 2-5 epilogue
-constexpr int ENGINE_SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
+constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int ENGINE_THREADS = 64 + EPI_THREADS;   // warp0 TMA, warp1 UMMA, warps 2.. epilogue
+constexpr int ENGINE_SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, scalars*/;
 
 enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
 

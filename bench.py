@@ -176,6 +176,8 @@ def run_ours(args, w, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from sdrm_b200 import _lib as _l
+    _l.load().sdrm_set_cluster_override(args.cluster)
     for i in range(args.warmup):
         step(1000 + i)
     eng = engine_for(diff, dev)
@@ -248,7 +250,7 @@ def run_ours(args, w, rank, world, local_rank):
                        **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
                        "l2": "each step writes n*I*4 bytes of logits (>> 126 MB L2 for cfg5); no reuse across steps",
                        "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
-            "clocks": clock_info, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -268,6 +270,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cluster", type=int, default=0, help="force the weight-multicast cluster size (1, 2, 4); 0 = auto")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

@@ -25,6 +25,10 @@ SIGNATURES = {
     "sdrm_last_launch_count": (C.c_int, [_P]),
     "sdrm_check_device_error": (C.c_int, [_P, _P]),
     "sdrm_probe_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "sdrm_probe_set_repeat": (None, [C.c_int]),
+    "sdrm_set_cluster_override": (None, [C.c_int]),
+    "sdrm_debug_set_trace": (None, [_P]),
+    "sdrm_last_cluster_size": (C.c_int, [_P]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "sdrm_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),
     "sdrm_topk_f64": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),

@@ -6,8 +6,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libsdrm_b200.so")
-SOURCES = ["errors.cu", "layer_engine.cu", "engine_host.cu", "metrics.cu", "train_kernels.cu"]
-HEADERS = ["ptx_sm100.cuh", "philox.cuh", "layer_engine.cuh", "host_util.h", "../../include/sdrm_b200.h"]
+SOURCES = ["errors.cu", "engine_host.cu", "metrics.cu", "train_kernels.cu"]
+HEADERS = ["ptx_sm100.cuh", "philox.cuh", "layer_engine.cuh", "layer_engine_kernel.cuh", "host_util.h",
+           "../../include/sdrm_b200.h"]
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",

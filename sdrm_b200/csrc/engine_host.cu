@@ -11,11 +11,10 @@
 #include "../../include/sdrm_b200.h"
 #include "host_util.h"
 #include "layer_engine.cuh"
+#include "layer_engine_kernel.cuh"
 #include "ptx_sm100.cuh"
 
 namespace sdrm {
-
-__global__ void sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P);
 
 // ------------------------------------------------------------------------------------------------
 // geometry of one dense layer on the engine
@@ -173,6 +172,8 @@ struct sdrm_handle {
   int device = 0;
   int num_sms = 0;
   int last_launches = 0;
+  int last_cluster = 1;
+  int resident[5] = {0, 0, 0, 0, 0};  // resident CTAs per cluster size
   int* err_word = nullptr;
   // denoiser
   bool have_den = false;
@@ -203,14 +204,53 @@ static void free_dec(sdrm_handle* h) {
   h->have_dec = false;
 }
 
+static int g_cluster_override = 0;  // 0 = automatic
+static unsigned long long* g_trace = nullptr;  // debug timeline buffer (device), see sdrm_debug_set_trace
+
 static int engine_set_smem_attr() {
   static bool done[64] = {false};
   int dev = 0;
   SDRM_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return SDRM_OK;
-  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   if (dev < 64) done[dev] = true;
+  return SDRM_OK;
+}
+
+// resident CTAs for a cluster size (1 CTA per SM; clusters must fit inside a GPC)
+static int max_resident_ctas(int cluster, int num_sms) {
+  if (cluster == 1) return num_sms;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(num_sms / cluster * cluster));
+  cfg.blockDim = dim3(ENGINE_THREADS);
+  cfg.dynamicSmemBytes = ENGINE_SMEM_BYTES;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  int n = 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<true>, &cfg);
+  if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n * cluster;
+}
+
+static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st) {
+  if (cluster == 1) {
+    sdrm_layer_engine_kernel<false><<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
+    SDRM_CUDA(cudaGetLastError());
+    return SDRM_OK;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  cfg.blockDim = dim3(ENGINE_THREADS);
+  cfg.dynamicSmemBytes = ENGINE_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<true>, P));
   return SDRM_OK;
 }
 
@@ -241,6 +281,9 @@ int sdrm_create(sdrm_handle** out, int device) {
   h->num_sms = prop.multiProcessorCount;
   SDRM_CUDA(cudaMalloc(&h->err_word, sizeof(int)));
   SDRM_CUDA(cudaMemset(h->err_word, 0, sizeof(int)));
+  if (engine_set_smem_attr() != SDRM_OK) { delete h; return SDRM_ERR_CUDA; }
+  h->resident[1] = h->num_sms;
+  h->resident[2] = max_resident_ctas(2, h->num_sms);
   *out = h;
   return SDRM_OK;
 }
@@ -336,7 +379,8 @@ static int kb_max_of(const sdrm_handle* h) {
 
 static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* act_bytes, size_t* stride) {
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
-  *grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, h->num_sms)));
+  // upper bound over every cluster choice (a cluster launch rounds the grid up to a multiple of the cluster size)
+  *grid = static_cast<int>(std::max<long long>(4, std::min<long long>((n_tiles + 3) / 4 * 4, (h->num_sms + 3) / 4 * 4)));
   *act_bytes = static_cast<size_t>(kb_max_of(h)) * A_TILE_BYTES;
   const int Lg16 = (h->L + 15) / 16;
   const size_t xs = static_cast<size_t>(Lg16) * 4 * TILE_M * 16;
@@ -399,8 +443,24 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.scratch_stride = stride;
   P.act_buf_bytes = act;
   P.err_word = h->err_word;
-  sdrm_layer_engine_kernel<<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
-  SDRM_CUDA(cudaGetLastError());
+  P.trace = g_trace;
+  // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
+  const long long n_tiles = (n + TILE_M - 1) / TILE_M;
+  int cluster = 1;
+  if (d_t_start == nullptr) cluster = n_tiles >= 2 ? 2 : 1;   // cta_group::2 pair: full-resolution chains only
+  if (g_cluster_override > 0 && (d_t_start == nullptr || g_cluster_override == 1)) cluster = g_cluster_override;
+  int launch_grid = 0;
+  for (; cluster >= 1; cluster >>= 1) {
+    const int resident = h->resident[cluster];
+    if (resident <= 0) continue;
+    const long long want = (n_tiles + cluster - 1) / cluster * cluster;
+    launch_grid = static_cast<int>(std::min<long long>(want, resident));
+    break;
+  }
+  if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
+  h->last_cluster = cluster;
+  rc = launch_engine(P, launch_grid, cluster, st);
+  if (rc) return rc;
   h->last_launches = 1;
   return SDRM_OK;
 }
@@ -433,6 +493,12 @@ static void probe_geometry(int64_t M, int K, int N, Geom* g, size_t* act, size_t
   *s_off = off; off += static_cast<size_t>(n_tiles) * 2 * (*act);
   *total = off;
 }
+
+static int g_probe_repeat = 1;
+void sdrm_probe_set_repeat(int n) { g_probe_repeat = n < 1 ? 1 : n; }
+void sdrm_debug_set_trace(void* d_buf) { g_trace = static_cast<unsigned long long*>(d_buf); }
+void sdrm_set_cluster_override(int c) { g_cluster_override = (c == 1 || c == 2) ? c : 0; }
+int sdrm_last_cluster_size(const sdrm_handle* h) { return h ? h->last_cluster : 0; }
 
 size_t sdrm_probe_linear_workspace_bytes(int64_t M, int K, int N) {
   if (M <= 0 || K <= 0 || N <= 0) return 0;
@@ -477,8 +543,10 @@ int sdrm_probe_linear(const float* d_A, const float* d_W, const float* d_bias, f
   P.scratch = ws + s_off; P.scratch_stride = 2 * act; P.act_buf_bytes = act;
   P.err_word = reinterpret_cast<int*>(ws);
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, sms)));
-  sdrm_layer_engine_kernel<<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
-  SDRM_CUDA(cudaGetLastError());
+  for (int rep = 0; rep < g_probe_repeat; ++rep) {
+    rc = launch_engine(P, grid, 1, st);
+    if (rc) return rc;
+  }
   return SDRM_OK;
 }
 

@@ -62,6 +62,8 @@ struct ChainParams {
   size_t scratch_stride;  // bytes per CTA
   size_t act_buf_bytes;   // bytes of one activation buffer (KBmax * A_TILE_BYTES)
   int* err_word;
+  unsigned long long* trace;  // debug: [3 roles][TRACE_CAP] (event code << 56 | globaltimer ns), CTA 0 only; or nullptr
 };
+constexpr int TRACE_CAP = 8192;
 
 }  // namespace sdrm

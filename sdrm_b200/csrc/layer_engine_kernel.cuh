@@ -13,6 +13,7 @@
 //   * warp 0 = TMA producer, warp 1 = UMMA issuer (one elected thread), warps 2-17 = epilogue; the epilogue
 //     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
 // Rows are independent, so there is no inter-CTA synchronisation anywhere.
+#pragma once
 #include "layer_engine.cuh"
 #include "philox.cuh"
 #include "ptx_sm100.cuh"
@@ -21,16 +22,6 @@ namespace sdrm {
 
 namespace {
 
-struct SmemLayout {
-  uint32_t stage_a[NUM_STAGES];
-  uint32_t stage_w[NUM_STAGES];
-  uint32_t full[NUM_STAGES];
-  uint32_t empty[NUM_STAGES];
-  uint32_t acc_full[2];
-  uint32_t acc_empty[2];
-  uint32_t act_ready;
-  uint32_t tile_ready;
-};
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
@@ -51,62 +42,82 @@ __device__ __forceinline__ float4* xstate_ptr(float* xs, int g16, int j, int r) 
 
 }  // namespace
 
+// PAIR = false: one CTA per row tile, tcgen05 cta_group::1, 4 stages of (A 16 KB + W 32 KB).
+// PAIR = true : two CTAs (a thread-block cluster of 2 = one TPC) work as a tcgen05 cta_group::2 pair on TWO row tiles
+//               (UMMA M = 256): each CTA stages its own A tile and only HALF of every weight k-block, so a stage is
+//               32 KB and 6 of them fit -> 50 % more k-blocks in flight per SM, and half the weight bytes per SM.
+//               The L2 round trip under load (~1.5 us) times the bytes per k-block is what bounds this kernel
+//               (Little's law on 192 KB of staging), which is why the pair mode is the fast path.
+template <bool PAIR>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
+  constexpr int NSTG = PAIR ? 6 : 4;
+  constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
+  constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
+  constexpr int NCTA = PAIR ? 2 : 1;
+  static_assert(NSTG * STG_BYTES == NUM_STAGES * STAGE_BYTES, "both modes use the same staging footprint");
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_addr - raw_addr);
-
-  SmemLayout S;
-#pragma unroll
-  for (int s = 0; s < NUM_STAGES; ++s) {
-    S.stage_a[s] = base_addr + s * STAGE_BYTES;
-    S.stage_w[s] = S.stage_a[s] + A_TILE_BYTES;
-  }
-  const uint32_t bar_base = base_addr + NUM_STAGES * STAGE_BYTES;
-#pragma unroll
-  for (int s = 0; s < NUM_STAGES; ++s) {
-    S.full[s] = bar_base + 8 * s;
-    S.empty[s] = bar_base + 8 * (NUM_STAGES + s);
-  }
-  S.acc_full[0] = bar_base + 8 * (2 * NUM_STAGES + 0);
-  S.acc_full[1] = bar_base + 8 * (2 * NUM_STAGES + 1);
-  S.acc_empty[0] = bar_base + 8 * (2 * NUM_STAGES + 2);
-  S.acc_empty[1] = bar_base + 8 * (2 * NUM_STAGES + 3);
-  S.act_ready = bar_base + 8 * (2 * NUM_STAGES + 4);
-  S.tile_ready = bar_base + 8 * (2 * NUM_STAGES + 5);
-  uint8_t* misc = smem + NUM_STAGES * STAGE_BYTES + 8 * (2 * NUM_STAGES + 6);
+  const uint32_t bar_base = base_addr + NSTG * STG_BYTES;
+  // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | peer_full[NSTG] | acc_full[2] | acc_empty[2] | act_ready | tile_ready
+  auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
+  auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
+  auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](uint32_t s) { return bar_base + 8u * (NSTG + s); };
+  auto bar_peer_full = [&](uint32_t s) { return bar_base + 8u * (2 * NSTG + s); };
+  auto bar_acc_full = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + b); };
+  auto bar_acc_empty = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + 2 + b); };
+  const uint32_t bar_act_ready = bar_base + 8u * (3 * NSTG + 4);
+  const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 5);
+  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 6);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NUM_STAGES; ++s) {
-      mbar_init(S.full[s], 1);
-      mbar_init(S.empty[s], 1);
+    for (int s = 0; s < NSTG; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_peer_full(s), 1);
     }
-    mbar_init(S.acc_full[0], 1);
-    mbar_init(S.acc_full[1], 1);
-    mbar_init(S.acc_empty[0], EPI_WARPS);
-    mbar_init(S.acc_empty[1], EPI_WARPS);
-    mbar_init(S.act_ready, EPI_WARPS);
-    mbar_init(S.tile_ready, EPI_WARPS);
+    mbar_init(bar_acc_full(0), 1);
+    mbar_init(bar_acc_full(1), 1);
+    mbar_init(bar_acc_empty(0), EPI_WARPS * NCTA);   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
+    mbar_init(bar_acc_empty(1), EPI_WARPS * NCTA);
+    mbar_init(bar_act_ready, EPI_WARPS);
+    mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anyone commits / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const long long n_tiles = (P.n_rows + TILE_M - 1) / TILE_M;
+  const long long n_clusters = gridDim.x / NCTA;
+  const long long my_cluster = blockIdx.x / NCTA;
+  // both CTAs of a pair run the same number of tile iterations (a ghost tile past n_tiles has no valid row)
+  const int n_iters = static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);
+  auto tile_of = [&](int it) -> long long { return (static_cast<long long>(it) * n_clusters + my_cluster) * NCTA + cta_rank; };
   int* err = P.err_word;
+  int trace_n = 0;
+  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp >= 2);
+  unsigned long long trace_seq = 0;  // k-block sequence number of the role (for matching producer / consumer events)
+  auto TR = [&](int role, unsigned long long code) {
+    if (tracing && trace_n < TRACE_CAP)
+      P.trace[role * TRACE_CAP + trace_n++] = (code << 56) | ((trace_seq & 0xFFFFull) << 40) | (globaltimer_ns() & 0xFFFFFFFFFFull);
+  };
 
   auto scratch_of = [&](long long tile) -> uint8_t* {
     const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x);
@@ -117,34 +128,47 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // ======================================= TMA producer =======================================
     if (lane == 0) {
       uint32_t stage = 0, sphase = 0, act_par = 0;
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(S.tile_ready, it & 1, err, WD_PRODUCER_TILE);
+      for (int it = 0; it < n_iters; ++it) {
+        const long long tile = tile_of(it);
+        if (!PAIR && tile >= n_tiles) break;
+        mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
         const int T_tile = tile_T[it & 1];
         const uint8_t* sc = scratch_of(tile);
         bool first = true;
         auto run = [&](const LayerDesc& ld) {
+          TR(0, 1);
           if (!first) {
-            mbar_wait(S.act_ready, act_par, err, WD_PRODUCER_ACT);
+            mbar_wait(bar_act_ready, act_par, err, WD_PRODUCER_ACT);
             act_par ^= 1;
           }
+          TR(0, 2);
           first = false;
           const uint8_t* a_hi = sc + static_cast<size_t>(ld.in_hi) * P.act_buf_bytes;
           const uint8_t* a_lo = sc + static_cast<size_t>(ld.in_lo) * P.act_buf_bytes;
-          const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;
+          const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;       // one whole weight k-block image
+          const uint32_t w_mine = PAIR ? w_bytes / 2 : w_bytes;               // the N-half this CTA feeds to the pair UMMA
+          const uint32_t w_off = PAIR ? cta_rank * w_mine : 0u;
+          const uint32_t tx = A_TILE_BYTES + w_mine;
           for (int c = 0; c < ld.NCH; ++c) {
             for (int p = 0; p < ld.passes; ++p) {
               const uint8_t* a_src = (p == 2) ? a_lo : a_hi;
               const int which = (p == 1) ? 1 : 0;
-              const uint8_t* w_src = ld.w_img + (static_cast<size_t>(which) * ld.NCH + c) * ld.KB * w_bytes;
+              const uint8_t* w_src = ld.w_img + (static_cast<size_t>(which) * ld.NCH + c) * ld.KB * w_bytes + w_off;
               for (int kb = 0; kb < ld.KB; ++kb) {
-                mbar_wait(S.empty[stage], sphase ^ 1, err, WD_PRODUCER_EMPTY);
-                mbar_arrive_expect_tx(S.full[stage], A_TILE_BYTES + w_bytes);
-                bulk_g2s(S.stage_a[stage], a_src + static_cast<size_t>(kb) * A_TILE_BYTES, A_TILE_BYTES, S.full[stage]);
-                bulk_g2s(S.stage_w[stage], w_src + static_cast<size_t>(kb) * w_bytes, w_bytes, S.full[stage]);
-                if (++stage == NUM_STAGES) { stage = 0; sphase ^= 1; }
+                mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
+                TR(0, 4);
+                const uint32_t fb = bar_full(stage);
+                mbar_arrive_expect_tx(fb, tx);
+                bulk_g2s(stage_w(stage), w_src, w_mine, fb);
+                bulk_g2s(stage_a(stage), a_src, A_TILE_BYTES, fb);
+                w_src += w_bytes;
+                a_src += A_TILE_BYTES;
+                TR(0, 5);
+                ++trace_seq;
+                if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
             }
+            TR(0, 3);
           }
         };
         for (int i = T_tile; i >= 1; --i)
@@ -153,38 +177,63 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       }
     }
   } else if (warp == 1) {
-    // ======================================= UMMA issuer ========================================
-    if (lane == 0) {
+    if (lane == 0 && PAIR && cta_rank != 0) {
+      // ============================== peer CTA: relay "my stage is full" to the leader ==============
+      uint32_t stage = 0, sphase = 0;
+      long long kb_per_step = 0, kb_dec = 0;
+      for (int l = 0; l < P.n_step; ++l) kb_per_step += static_cast<long long>(P.step[l].NCH) * P.step[l].passes * P.step[l].KB;
+      for (int l = 0; l < P.n_dec; ++l) kb_dec += static_cast<long long>(P.dec[l].NCH) * P.dec[l].passes * P.dec[l].KB;
+      const long long total = static_cast<long long>(n_iters) * (kb_per_step * P.T + kb_dec);
+      for (long long i = 0; i < total; ++i) {
+        mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
+        mbar_arrive_cluster(mapa_cluster(bar_peer_full(stage), 0));
+        if (++stage == NSTG) { stage = 0; sphase ^= 1; }
+      }
+    } else if (lane == 0) {
+      // ======================================= UMMA issuer ========================================
       uint32_t stage = 0, sphase = 0, cc = 0;
-      int it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        mbar_wait(S.tile_ready, it & 1, err, WD_MMA_TILE);
-        const int T_tile = tile_T[it & 1];
+      for (int it = 0; it < n_iters; ++it) {
+        if (!PAIR && tile_of(it) >= n_tiles) break;
+        int T_tile = P.T;   // the pair mode only runs full-resolution chains (same T for both row tiles)
+        if (!PAIR) {
+          mbar_wait(bar_tile_ready, it & 1, err, WD_MMA_TILE);
+          T_tile = tile_T[it & 1];
+        }
         auto run = [&](const LayerDesc& ld) {
-          const uint32_t idesc = umma_idesc_bf16(TILE_M, ld.NC);
+          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ld.NC);
           for (int c = 0; c < ld.NCH; ++c) {
             const uint32_t buf = cc & 1u;
-            mbar_wait(S.acc_empty[buf], ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
+            TR(1, 1);
+            mbar_wait(bar_acc_empty(buf), ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
             tc_fence_after();
+            TR(1, 2);
             const uint32_t d_tmem = tmem_base + buf * 256u;
             uint32_t acc = 0;
             for (int p = 0; p < ld.passes; ++p) {
               for (int kb = 0; kb < ld.KB; ++kb) {
-                mbar_wait(S.full[stage], sphase, err, WD_MMA_FULL);
+                mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
+                if (PAIR) mbar_wait(bar_peer_full(stage), sphase, err, WD_MMA_FULL);
                 tc_fence_after();
-                const uint64_t a_desc = umma_desc_sw128(S.stage_a[stage]);
-                const uint64_t b_desc = umma_desc_sw128(S.stage_w[stage]);
+                TR(1, kb == 0 && p == 0 ? 3 : 5);
+                const uint64_t a_desc = umma_desc_sw128(stage_a(stage));
+                const uint64_t b_desc = umma_desc_sw128(stage_w(stage));
                 const int nk = (kb == ld.KB - 1) ? ld.kmma_last : 4;
                 for (int k = 0; k < nk; ++k) {
                   // +32 B (16 bf16) along K inside the swizzle row = +2 in the 16-byte address field
-                  umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
+                  if (PAIR) umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
+                  else umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
                   acc = 1;
                 }
-                umma_commit(S.empty[stage]);
-                if (++stage == NUM_STAGES) { stage = 0; sphase ^= 1; }
+                if (PAIR) umma_commit_pair(bar_empty(stage), 0x3);
+                else umma_commit(bar_empty(stage));
+                TR(1, 6);
+                ++trace_seq;
+                if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
             }
-            umma_commit(S.acc_full[buf]);
+            if (PAIR) umma_commit_pair(bar_acc_full(buf), 0x3);
+            else umma_commit(bar_acc_full(buf));
+            TR(1, 4);
             ++cc;
           }
         };
@@ -217,7 +266,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     int noise_slots_per_step = 0;
     for (int l = 0; l + 1 < P.n_step; ++l) noise_slots_per_step += P.step[l].NCH;
 
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (; it < n_iters; ++it) {
+      const long long tile = tile_of(it);
+      if (!PAIR && tile >= n_tiles) break;
       uint8_t* sc = scratch_of(tile);
       float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
       const long long prow = tile * TILE_M + r;   // physical row of this launch
@@ -327,7 +378,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       if (warp == 2 && lane == 0) tile_T[it & 1] = T_tile;
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(S.tile_ready);
+      if (lane == 0) mbar_arrive(bar_tile_ready);
 
       int noise_done = noise_total;   // the tile's first step got its noise in the init above
       int noise_slots = 0;
@@ -351,8 +402,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int ngroups = ld.NC >> 4;
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
-          mbar_wait(S.acc_full[buf], (cc >> 1) & 1u, err, WD_EPI_ACC);
+          if (warp == 2 && lane == 0) TR(2, 1);
+          mbar_wait(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC);
           tc_fence_after();
+          if (warp == 2 && lane == 0) TR(2, 2);
           for (int g = sub; g < ngroups; g += EPI_SUB) {
             uint32_t v[16];
             tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
@@ -454,19 +507,25 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(S.acc_empty[buf]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), 0));   // the leader CTA issues the UMMAs
+            else mbar_arrive(bar_acc_empty(buf));
+          }
+          if (warp == 2 && lane == 0) TR(2, 3);
           ++cc;
           // spare time while the tensor core works on the next chunk: a slice of this step's noise
           if (ld.kind == EPI_PRELU && noise_slots > 0) {
             const int todo = (noise_total - noise_done + noise_slots - 1) / noise_slots;
             for (int k = 0; k < todo; ++k) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
             --noise_slots;
+            if (warp == 2 && lane == 0) TR(2, 4);
           }
         }
         if (!last_of_tile) {
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) mbar_arrive(S.act_ready);
+          if (lane == 0) mbar_arrive(bar_act_ready);
+          if (warp == 2 && lane == 0) TR(2, 5);
         }
       };
       for (int i = T_tile; i >= 1; --i)
@@ -478,9 +537,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its operands
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 

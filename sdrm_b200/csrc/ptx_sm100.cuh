@@ -51,16 +51,21 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #define SDRM_WATCHDOG_NS 4000000000ull
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_word, int code) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
+  // Fast path: plain polling (try_wait itself suspends the thread for a bounded time).  No timer is touched until
+  // the wait has lasted implausibly long: %globaltimer / clock reads on the hot path cost far more than the poll.
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0) {
-      if (globaltimer_ns() - t0 > SDRM_WATCHDOG_NS) {
-        if (err_word) atomicCAS(err_word, 0, code);
-        __threadfence_system();
-        __trap();
+    if (++spins == (1u << 16)) {
+      const uint64_t t0 = globaltimer_ns();
+      uint32_t slow = 0;
+      while (!mbar_try_wait(bar, parity)) {
+        if ((++slow & 0xfff) == 0 && globaltimer_ns() - t0 > SDRM_WATCHDOG_NS) {
+          if (err_word) atomicCAS(err_word, 0, code);
+          __threadfence_system();
+          __trap();
+        }
       }
+      return;
     }
   }
 }
@@ -72,6 +77,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
+      : "memory");
+}
+// same, multicast: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`, and complete_tx is
+// signalled on the mbarrier at the same offset in each of them
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
       : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
@@ -103,6 +117,16 @@ __device__ __forceinline__ void tmem_relinquish() {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// cta_group::2 variants: one warp of EACH CTA of the pair executes alloc / dealloc
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -139,6 +163,46 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
 // all previously issued UMMAs of this thread arrive on `bar` when they retire
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// cta_group::2: issued by the leader CTA only; A rows 0-127 / 128-255 and the two N-halves of B come from the shared
+// memory of CTA 0 / CTA 1 at the same CTA-relative offsets, D lands in each CTA's own TMEM (its 128 rows).
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // 32 lanes x 16 consecutive fp32 columns: thread t of the warp reads TMEM lane (base_lane + t)

@@ -83,6 +83,24 @@ def test_partition_invariance():
     assert torch.equal(whole, torch.cat([a, b]))
 
 
+def test_single_and_pair_mode_are_bit_identical():
+    """The weight stream chain runs on single CTAs (cta_group::1) or CTA pairs (cta_group::2, UMMA M=256); rows do not change."""
+    from sdrm_b200 import _lib
+    lib = _lib.load()
+    n, I, H, L, T, nh, nd = 1500, 700, 200, 264, 7, 2, 1.0     # 12 row tiles; ragged last tile; ghost tiles for cluster 4
+    diff, vae = random_modules(I, H, L, T, nh, seed=6, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    outs = {}
+    try:
+        for c in (1, 2):
+            lib.sdrm_set_cluster_override(c)
+            outs[c] = eng.sample(n, seed=77, check=True).clone()
+            assert lib.sdrm_last_cluster_size(eng.handle) == c
+    finally:
+        lib.sdrm_set_cluster_override(0)
+    assert torch.equal(outs[1], outs[2])
+
+
 def test_random_mode_matches_oracle():
     from oracle import philox_ref
     from oracle import sdrm_oracle as orc

@@ -178,6 +178,7 @@ def run_ours(args, w, rank, world, local_rank):
 
     from sdrm_b200 import _lib as _l
     _l.load().sdrm_set_cluster_override(args.cluster)
+    _l.load().sdrm_debug_set_flags(int(os.environ.get("SDRM_DEBUG_FLAGS", "0")))
     for i in range(args.warmup):
         step(1000 + i)
     eng = engine_for(diff, dev)

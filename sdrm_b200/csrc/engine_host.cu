@@ -205,6 +205,7 @@ static void free_dec(sdrm_handle* h) {
 }
 
 static int g_cluster_override = 0;  // 0 = automatic
+static int g_debug_flags = 0;
 static unsigned long long* g_trace = nullptr;  // debug timeline buffer (device), see sdrm_debug_set_trace
 
 static int engine_set_smem_attr() {
@@ -307,6 +308,8 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
   if (nh > 0 && (!d_Wh || !d_bh || !d_ah)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: nh>0 needs Wh,bh,ah");
   if (T < 1 || L < 1 || D < 1 || nh < 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: bad shape");
   if (2 + nh > MAX_STEP_LAYERS) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: nh > 6");
+  if (L > MAX_ACT_CHUNKS * MAX_NC || D > MAX_ACT_CHUNKS * MAX_NC)
+    return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: latent / hidden width above 2048");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
   const bool same = h->have_den && h->T == T && h->L == L && h->D == D && h->nh == nh;
@@ -344,6 +347,7 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
                       int L, int H, int I, void* stream) {
   if (!h || !d_W1 || !d_b1 || !d_W2 || !d_b2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: null pointer");
   if (L < 1 || H < 1 || I < 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: bad shape");
+  if (H > MAX_ACT_CHUNKS * MAX_NC) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_decoder_pack: VAE hidden width above 2048");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
   const bool same = h->have_dec && h->g1.K == L && h->H == H && h->I == I;
@@ -444,6 +448,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.act_buf_bytes = act;
   P.err_word = h->err_word;
   P.trace = g_trace;
+  P.debug_flags = g_debug_flags;
   // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
@@ -496,6 +501,7 @@ static void probe_geometry(int64_t M, int K, int N, Geom* g, size_t* act, size_t
 
 static int g_probe_repeat = 1;
 void sdrm_probe_set_repeat(int n) { g_probe_repeat = n < 1 ? 1 : n; }
+void sdrm_debug_set_flags(int f) { g_debug_flags = f; }
 void sdrm_debug_set_trace(void* d_buf) { g_trace = static_cast<unsigned long long*>(d_buf); }
 void sdrm_set_cluster_override(int c) { g_cluster_override = (c == 1 || c == 2) ? c : 0; }
 int sdrm_last_cluster_size(const sdrm_handle* h) { return h ? h->last_cluster : 0; }

@@ -14,10 +14,12 @@ constexpr int STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES_MAX;
 constexpr int NUM_STAGES = 4;
 constexpr int MAX_STEP_LAYERS = 8;                 // 2 + nh, nh <= 6
 constexpr int NUM_ACT_BUFS = 4;
+constexpr int MAX_ACT_CHUNKS = 8;                  // N chunks of an activation-producing layer (features <= 2048)
 constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
 constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int ENGINE_THREADS = 64 + EPI_THREADS;   // warp0 TMA, warp1 UMMA, warps 2.. epilogue
+constexpr int CTRL_WARPS = 3;                      // warp0 weight producer, warp1 UMMA issuer, warp2 activation producer
+constexpr int ENGINE_THREADS = CTRL_WARPS * 32 + EPI_THREADS;
 constexpr int ENGINE_SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, scalars*/;
 
 enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
@@ -62,6 +64,7 @@ struct ChainParams {
   size_t scratch_stride;  // bytes per CTA
   size_t act_buf_bytes;   // bytes of one activation buffer (KBmax * A_TILE_BYTES)
   int* err_word;
+  int debug_flags;            // perf experiments only: 1 = skip activation stores, 2 = skip fp32 state traffic, 4 = skip noise
   unsigned long long* trace;  // debug: [3 roles][TRACE_CAP] (event code << 56 | globaltimer ns), CTA 0 only; or nullptr
 };
 constexpr int TRACE_CAP = 8192;

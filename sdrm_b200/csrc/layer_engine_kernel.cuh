@@ -10,7 +10,8 @@
 //   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
 //     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the
 //     bf16 (or bf16 hi/lo) re-quantisation, and write the next layer's A images (L2-resident scratch);
-//   * warp 0 = TMA producer, warp 1 = UMMA issuer (one elected thread), warps 2-17 = epilogue; the epilogue
+//   * warp 0 = weight TMA producer, warp 1 = UMMA issuer (one elected thread), warp 2 = activation TMA producer,
+//     warps 3-18 = epilogue; the epilogue
 //     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
 // Rows are independent, so there is no inter-CTA synchronisation anywhere.
 #pragma once
@@ -26,7 +27,8 @@ namespace {
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // write 16 consecutive bf16 features [f0, f0+16) of tile row r into a k-block image buffer
-__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8]) {
+__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8], bool skip = false) {
+  if (skip) return;
   const int kb = f0 >> 6;
   const int j0 = (f0 & 63) >> 3;
   uint8_t* base = buf + static_cast<size_t>(kb) * A_TILE_BYTES + r * 128;
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_addr - raw_addr);
   const uint32_t bar_base = base_addr + NSTG * STG_BYTES;
-  // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | peer_full[NSTG] | acc_full[2] | acc_empty[2] | act_ready | tile_ready
+  // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | peer_full[NSTG] | acc_full[2] | acc_empty[2] | tile_ready |
+  //                             act_chunk[MAX_ACT_CHUNKS]
   auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
   auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
   auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -69,9 +72,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   auto bar_peer_full = [&](uint32_t s) { return bar_base + 8u * (2 * NSTG + s); };
   auto bar_acc_full = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + b); };
   auto bar_acc_empty = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + 2 + b); };
-  const uint32_t bar_act_ready = bar_base + 8u * (3 * NSTG + 4);
-  const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 5);
-  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 6);
+  const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 4);
+  // one barrier per chunk INDEX: chunk c of layer l+1 cannot finish before the A producer consumed chunk c of layer l,
+  // so a waiter never lags more than one phase (a single barrier would be lapped by fast chunk epilogues)
+  auto bar_act_chunk = [&](uint32_t c) { return bar_base + 8u * (3 * NSTG + 5 + c); };
+  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 5 + MAX_ACT_CHUNKS);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NSTG; ++s) {
-      mbar_init(bar_full(s), 1);
+      mbar_init(bar_full(s), 2);     // weight producer + activation producer each arm their own byte count
       mbar_init(bar_empty(s), 1);
       mbar_init(bar_peer_full(s), 1);
     }
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_acc_full(1), 1);
     mbar_init(bar_acc_empty(0), EPI_WARPS * NCTA);   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
     mbar_init(bar_acc_empty(1), EPI_WARPS * NCTA);
-    mbar_init(bar_act_ready, EPI_WARPS);
+    for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(c), EPI_WARPS);
     mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
@@ -112,10 +117,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   auto tile_of = [&](int it) -> long long { return (static_cast<long long>(it) * n_clusters + my_cluster) * NCTA + cta_rank; };
   int* err = P.err_word;
   int trace_n = 0;
-  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp >= 2);
+  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp >= CTRL_WARPS);
   unsigned long long trace_seq = 0;  // k-block sequence number of the role (for matching producer / consumer events)
+  const bool trace_kb = (P.debug_flags & 8) != 0;   // per-k-block events perturb the pipeline; off by default
   auto TR = [&](int role, unsigned long long code) {
-    if (tracing && trace_n < TRACE_CAP)
+    if (tracing && trace_n < TRACE_CAP && (trace_kb || !((role == 0 && (code == 4 || code == 5)) || (role == 1 && code >= 5))))
       P.trace[role * TRACE_CAP + trace_n++] = (code << 56) | ((trace_seq & 0xFFFFull) << 40) | (globaltimer_ns() & 0xFFFFFFFFFFull);
   };
 
@@ -124,31 +130,34 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
   };
 
-  if (warp == 0) {
-    // ======================================= TMA producer =======================================
+  if (warp == 0 || warp == 2) {
+    // ============================ TMA producers: warp 0 streams weights, warp 2 streams activations =========
+    // Two issuing threads halve the per-k-block issue latency of the ring; the weight stream does not depend on the
+    // previous layer's epilogue, so it runs ahead across layer boundaries.
     if (lane == 0) {
-      uint32_t stage = 0, sphase = 0, act_par = 0;
+      const bool is_w = (warp == 0);
+      uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier
       for (int it = 0; it < n_iters; ++it) {
         const long long tile = tile_of(it);
         if (!PAIR && tile >= n_tiles) break;
-        mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
-        const int T_tile = tile_T[it & 1];
+        int T_tile = P.T;
+        if (!is_w || !PAIR) {   // (single mode: T_tile may be per tile)
+          mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
+          T_tile = tile_T[it & 1];
+        }
         const uint8_t* sc = scratch_of(tile);
-        bool first = true;
+        // Readiness of this layer's input is tracked per CHUNK of the producing layer (one act_ready phase per chunk
+        // epilogue): k-block kb only needs the chunks covering features < 64 (kb + 1), so the next layer starts while the
+        // previous layer's last chunk is still in its epilogue.
+        int prev_nch = 0, prev_nc = 1;
         auto run = [&](const LayerDesc& ld) {
-          TR(0, 1);
-          if (!first) {
-            mbar_wait(bar_act_ready, act_par, err, WD_PRODUCER_ACT);
-            act_par ^= 1;
-          }
-          TR(0, 2);
-          first = false;
+          int ready = 0;
+          if (!is_w) TR(0, 1);
           const uint8_t* a_hi = sc + static_cast<size_t>(ld.in_hi) * P.act_buf_bytes;
           const uint8_t* a_lo = sc + static_cast<size_t>(ld.in_lo) * P.act_buf_bytes;
           const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;       // one whole weight k-block image
           const uint32_t w_mine = PAIR ? w_bytes / 2 : w_bytes;               // the N-half this CTA feeds to the pair UMMA
           const uint32_t w_off = PAIR ? cta_rank * w_mine : 0u;
-          const uint32_t tx = A_TILE_BYTES + w_mine;
           for (int c = 0; c < ld.NCH; ++c) {
             for (int p = 0; p < ld.passes; ++p) {
               const uint8_t* a_src = (p == 2) ? a_lo : a_hi;
@@ -156,20 +165,36 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const uint8_t* w_src = ld.w_img + (static_cast<size_t>(which) * ld.NCH + c) * ld.KB * w_bytes + w_off;
               for (int kb = 0; kb < ld.KB; ++kb) {
                 mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
-                TR(0, 4);
                 const uint32_t fb = bar_full(stage);
-                mbar_arrive_expect_tx(fb, tx);
-                bulk_g2s(stage_w(stage), w_src, w_mine, fb);
-                bulk_g2s(stage_a(stage), a_src, A_TILE_BYTES, fb);
-                w_src += w_bytes;
-                a_src += A_TILE_BYTES;
-                TR(0, 5);
-                ++trace_seq;
+                if (is_w) {
+                  mbar_arrive_expect_tx(fb, w_mine);
+                  bulk_g2s(stage_w(stage), w_src, w_mine, fb);
+                  w_src += w_bytes;
+                } else {
+                  if (c == 0 && p == 0) {
+                    int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
+                    if (need > prev_nch || kb == ld.KB - 1) need = prev_nch;
+                    while (ready < need) {
+                      mbar_wait(bar_act_chunk(ready), (act_par >> ready) & 1u, err, WD_PRODUCER_ACT);
+                      act_par ^= (1u << ready);
+                      ++ready;
+                    }
+                    if (kb == 0) TR(0, 2);
+                  }
+                  TR(0, 4);
+                  mbar_arrive_expect_tx(fb, A_TILE_BYTES);
+                  bulk_g2s(stage_a(stage), a_src, A_TILE_BYTES, fb);
+                  a_src += A_TILE_BYTES;
+                  TR(0, 5);
+                  ++trace_seq;
+                }
                 if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
             }
-            TR(0, 3);
+            if (!is_w) TR(0, 3);
           }
+          prev_nch = (ld.kind == EPI_LINEAR_OUT) ? 0 : ld.NCH;
+          prev_nc = ld.NC;
         };
         for (int i = T_tile; i >= 1; --i)
           for (int l = 0; l < P.n_step; ++l) run(P.step[l]);
@@ -177,17 +202,21 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && PAIR && cta_rank != 0) {
+    if (PAIR && cta_rank != 0) {
       // ============================== peer CTA: relay "my stage is full" to the leader ==============
-      uint32_t stage = 0, sphase = 0;
-      long long kb_per_step = 0, kb_dec = 0;
-      for (int l = 0; l < P.n_step; ++l) kb_per_step += static_cast<long long>(P.step[l].NCH) * P.step[l].passes * P.step[l].KB;
-      for (int l = 0; l < P.n_dec; ++l) kb_dec += static_cast<long long>(P.dec[l].NCH) * P.dec[l].passes * P.dec[l].KB;
-      const long long total = static_cast<long long>(n_iters) * (kb_per_step * P.T + kb_dec);
-      for (long long i = 0; i < total; ++i) {
-        mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
-        mbar_arrive_cluster(mapa_cluster(bar_peer_full(stage), 0));
-        if (++stage == NSTG) { stage = 0; sphase ^= 1; }
+      // One lane per stage: a remote release-arrive costs most of a microsecond, so the six stages are relayed by
+      // six independent lanes instead of one serial loop.
+      if (lane == 0) {
+        long long kb_per_step = 0, kb_dec = 0;
+        for (int l = 0; l < P.n_step; ++l) kb_per_step += static_cast<long long>(P.step[l].NCH) * P.step[l].passes * P.step[l].KB;
+        for (int l = 0; l < P.n_dec; ++l) kb_dec += static_cast<long long>(P.dec[l].NCH) * P.dec[l].passes * P.dec[l].KB;
+        const long long total = static_cast<long long>(n_iters) * (kb_per_step * P.T + kb_dec);
+        uint32_t stage = 0, ph = 0;
+        for (long long i = 0; i < total; ++i) {
+          mbar_wait(bar_full(stage), ph, err, WD_MMA_FULL);
+          mbar_arrive_cluster(mapa_cluster(bar_peer_full(stage), 0));
+          if (++stage == NSTG) { stage = 0; ph ^= 1; }
+        }
       }
     } else if (lane == 0) {
       // ======================================= UMMA issuer ========================================
@@ -212,7 +241,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             for (int p = 0; p < ld.passes; ++p) {
               for (int kb = 0; kb < ld.KB; ++kb) {
                 mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
-                if (PAIR) mbar_wait(bar_peer_full(stage), sphase, err, WD_MMA_FULL);
+                if (PAIR) { TR(1, 7); mbar_wait(bar_peer_full(stage), sphase, err, WD_MMA_FULL); }
                 tc_fence_after();
                 TR(1, kb == 0 && p == 0 ? 3 : 5);
                 const uint64_t a_desc = umma_desc_sw128(stage_a(stage));
@@ -248,7 +277,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // g = sub (mod 4).  One thread always touches the same (row, columns) of the fp32 state, so the state
     // needs no synchronisation at all.
     const int q = warp & 3;
-    const int sub = (warp - 2) >> 2;
+    const int sub = (warp - CTRL_WARPS) >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t cc = 0;
@@ -258,7 +287,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     if (!P.preloaded_input) {
       uint4* z = reinterpret_cast<uint4*>(scratch_of(blockIdx.x));
       const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
-      for (size_t i = threadIdx.x - 64; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (size_t i = threadIdx.x - CTRL_WARPS * 32; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       epi_bar_sync();
     }
     // noise groups of this thread per step: g = sub, sub + 4, ... < Lg16
@@ -282,7 +311,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       int m = t_row;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) warp_max[(it & 1) * EPI_WARPS + (warp - 2)] = m;
+      if (lane == 0) warp_max[(it & 1) * EPI_WARPS + (warp - CTRL_WARPS)] = m;
       epi_bar_sync();
       int T_tile = 0;
 #pragma unroll
@@ -308,6 +337,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       // Noise half of the posterior update, done AHEAD of the eps GEMM of the same step (z does not depend on the
       // network): state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
       auto noise_group = [&](int step, int g16) {
+        if (P.debug_flags & 4) return;
         const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
         const bool active = valid && (step <= t_row);
         if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
@@ -375,7 +405,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           noise_group(T_tile, g);
         }
       }
-      if (warp == 2 && lane == 0) tile_T[it & 1] = T_tile;
+      if (warp == CTRL_WARPS && lane == 0) tile_T[it & 1] = T_tile;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tile_ready);
@@ -402,10 +432,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int ngroups = ld.NC >> 4;
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
-          if (warp == 2 && lane == 0) TR(2, 1);
+          if (warp == CTRL_WARPS && lane == 0) TR(2, 1);
           mbar_wait(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC);
           tc_fence_after();
-          if (warp == 2 && lane == 0) TR(2, 2);
+          if (warp == CTRL_WARPS && lane == 0) TR(2, 2);
           for (int g = sub; g < ngroups; g += EPI_SUB) {
             uint32_t v[16];
             tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
@@ -430,7 +460,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 const float a1 = h[2 * e + 1] > 0.f ? h[2 * e + 1] : slope * h[2 * e + 1];
                 pk[e] = pack_bf16x2(a0, a1);
               }
-              store_act16(out_hi, r, f0, pk);
+              store_act16(out_hi, r, f0, pk, P.debug_flags & 1);
             } else if (ld.kind == EPI_POSTERIOR) {
               // x_{i-1} = (x_i - eps (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) nd z; the state already holds
               // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise_group), so only the eps term is left.
@@ -511,21 +541,22 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), 0));   // the leader CTA issues the UMMAs
             else mbar_arrive(bar_acc_empty(buf));
           }
-          if (warp == 2 && lane == 0) TR(2, 3);
+          if (warp == CTRL_WARPS && lane == 0) TR(2, 3);
           ++cc;
+          if (!last_of_tile && ld.kind != EPI_LINEAR_OUT) {
+            // this chunk's activations are complete: publish them to the TMA (async) proxy and tell the A producer
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act_chunk(c));
+            if (warp == CTRL_WARPS && lane == 0) TR(2, 5);
+          }
           // spare time while the tensor core works on the next chunk: a slice of this step's noise
           if (ld.kind == EPI_PRELU && noise_slots > 0) {
             const int todo = (noise_total - noise_done + noise_slots - 1) / noise_slots;
             for (int k = 0; k < todo; ++k) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
             --noise_slots;
-            if (warp == 2 && lane == 0) TR(2, 4);
+            if (warp == CTRL_WARPS && lane == 0) TR(2, 4);
           }
-        }
-        if (!last_of_tile) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_act_ready);
-          if (warp == 2 && lane == 0) TR(2, 5);
         }
       };
       for (int i = T_tile; i >= 1; --i)

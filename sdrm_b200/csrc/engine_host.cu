@@ -424,14 +424,15 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     d.KB = g.KB; d.kmma_last = g.kmma_last; d.passes = passes; d.NCH = g.NCH; d.NC = g.NC; d.kind = kind;
     d.in_hi = in_hi; d.in_lo = in_lo; d.out_hi = out_hi; d.out_lo = out_lo; d.n_valid = g.N;
   };
+  // chain layers ping-pong between activation buffers 0/1 (the kernel derives the parity); decoder descriptors name
+  // their hi buffers RELATIVE to the chain's last output (0 = that buffer, 1 = the other), lo buffers are 2 and 3
   int l = 0;
-  fill(P.step[l++], h->w0, h->bias0, h->slopes, h->g0.Np, h->g0, 1, EPI_PRELU, 2, 2, 0, 0);
-  for (int j = 0; j < h->nh; ++j)
-    fill(P.step[l++], h->wh, h->bh, h->slopes + 1, 0, h->gh, 1, EPI_PRELU, j & 1, j & 1, (j + 1) & 1, (j + 1) & 1);
-  fill(P.step[l++], h->wo, h->bo, nullptr, 0, h->go, 1, EPI_POSTERIOR, h->nh & 1, h->nh & 1, 2, 3);
+  fill(P.step[l++], h->w0, h->bias0, h->slopes, h->g0.Np, h->g0, 1, EPI_PRELU, 0, 0, 0, 0);
+  for (int j = 0; j < h->nh; ++j) fill(P.step[l++], h->wh, h->bh, h->slopes + 1, 0, h->gh, 1, EPI_PRELU, 0, 0, 0, 0);
+  fill(P.step[l++], h->wo, h->bo, nullptr, 0, h->go, 1, EPI_POSTERIOR, 0, 0, 0, 0);
   P.n_step = l;
-  fill(P.dec[0], h->w1, h->b1, nullptr, 0, h->g1, 3, EPI_TANH_SPLIT, 2, 3, 0, 1);
-  fill(P.dec[1], h->w2, h->b2, nullptr, 0, h->g2, 3, EPI_LINEAR_OUT, 0, 1, 0, 0);
+  fill(P.dec[0], h->w1, h->b1, nullptr, 0, h->g1, 3, EPI_TANH_SPLIT, 0, 2, 1, 3);
+  fill(P.dec[1], h->w2, h->b2, nullptr, 0, h->g2, 3, EPI_LINEAR_OUT, 1, 3, 0, 0);
   P.n_dec = 2;
   P.T = h->T; P.L = h->L; P.Lg16 = (h->L + 15) / 16;
   P.preloaded_input = 0;
@@ -452,7 +453,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
-  if (d_t_start == nullptr) cluster = n_tiles >= 2 ? 2 : 1;   // cta_group::2 pair: full-resolution chains only
+  // the cta_group::2 pair mode (full-resolution chains only) is opt-in via sdrm_set_cluster_override(2): with the
+  // relay-based stage hand-off it is still ~4 % slower than single-CTA mode on B200 (kernel K1)
   if (g_cluster_override > 0 && (d_t_start == nullptr || g_cluster_override == 1)) cluster = g_cluster_override;
   int launch_grid = 0;
   for (; cluster >= 1; cluster >>= 1) {

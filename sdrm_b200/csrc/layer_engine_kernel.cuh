@@ -150,11 +150,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         // epilogue): k-block kb only needs the chunks covering features < 64 (kb + 1), so the next layer starts while the
         // previous layer's last chunk is still in its epilogue.
         int prev_nch = 0, prev_nc = 1;
-        auto run = [&](const LayerDesc& ld) {
+        auto run = [&](const LayerDesc& ld, int in_hi_buf, int in_lo_buf) {
           int ready = 0;
           if (!is_w) TR(0, 1);
-          const uint8_t* a_hi = sc + static_cast<size_t>(ld.in_hi) * P.act_buf_bytes;
-          const uint8_t* a_lo = sc + static_cast<size_t>(ld.in_lo) * P.act_buf_bytes;
+          const uint8_t* a_hi = sc + static_cast<size_t>(in_hi_buf) * P.act_buf_bytes;
+          const uint8_t* a_lo = sc + static_cast<size_t>(in_lo_buf) * P.act_buf_bytes;
           const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;       // one whole weight k-block image
           const uint32_t w_mine = PAIR ? w_bytes / 2 : w_bytes;               // the N-half this CTA feeds to the pair UMMA
           const uint32_t w_off = PAIR ? cta_rank * w_mine : 0u;
@@ -196,9 +196,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           prev_nch = (ld.kind == EPI_LINEAR_OUT) ? 0 : ld.NCH;
           prev_nc = ld.NC;
         };
+        // chain layers ping-pong between activation buffers 0 and 1 (in = parity of the layer count so far); only two
+        // hot buffers per CTA keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
+        int cur = 0;
         for (int i = T_tile; i >= 1; --i)
-          for (int l = 0; l < P.n_step; ++l) run(P.step[l]);
-        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
+          for (int l = 0; l < P.n_step; ++l) { run(P.step[l], cur, cur); cur ^= 1; }
+        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
       }
     }
   } else if (warp == 1) {
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4* px = xstate_ptr(xs, g16, j, r);
-          const float4 xo = *px;
+          const float4 xo = __ldcs(px);   // streaming: the fp32 state must not evict the activation images from L2
           float z4[4] = {0.f, 0.f, 0.f, 0.f};
           if (sg != 0.0f) {
             if (P.inj_z) {
@@ -365,13 +368,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           o.y = (f + 1 < P.L) ? fmaf(sg, z4[1], xo.y * c2) : 0.0f;
           o.z = (f + 2 < P.L) ? fmaf(sg, z4[2], xo.z * c2) : 0.0f;
           o.w = (f + 3 < P.L) ? fmaf(sg, z4[3], xo.w * c2) : 0.0f;
-          *px = o;
+          __stcs(px, o);
         }
       };
 
       // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38); also the noise half of the first step
       if (P.n_step > 0) {
-        uint8_t* in0 = sc + static_cast<size_t>(P.step[0].in_hi) * P.act_buf_bytes;
+        uint8_t* in0 = sc;   // the first chain layer reads activation buffer 0
         for (int g = sub; g < P.Lg16; g += EPI_SUB) {
           float x[16];
 #pragma unroll
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const int f = g * 16 + j * 4 + e;
               x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;
             }
-            *xstate_ptr(xs, g, j, r) = make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]);
+            __stcs(xstate_ptr(xs, g, j, r), make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]));
           }
           const uint32_t keep = keep_mask16(T_tile, g);
           uint32_t pk[8];
@@ -414,9 +417,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       int noise_slots = 0;
 
       // ---- layers
-      auto run = [&](const LayerDesc& ld, int step, int layer_idx, bool last_of_tile) {
-        uint8_t* out_hi = sc + static_cast<size_t>(ld.out_hi) * P.act_buf_bytes;
-        uint8_t* out_lo = sc + static_cast<size_t>(ld.out_lo) * P.act_buf_bytes;
+      auto run = [&](const LayerDesc& ld, int step, int layer_idx, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
+        uint8_t* out_hi = sc + static_cast<size_t>(out_hi_buf) * P.act_buf_bytes;
+        uint8_t* out_lo = sc + static_cast<size_t>(out_lo_buf) * P.act_buf_bytes;
         const float* bias_row = ld.bias + static_cast<size_t>(step) * ld.bias_step_stride;
         const float slope = ld.slope ? __ldg(ld.slope) : 0.0f;
         float c12 = 0.f;
@@ -433,7 +436,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
           if (warp == CTRL_WARPS && lane == 0) TR(2, 1);
-          mbar_wait(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC);
+          mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 256);
           tc_fence_after();
           if (warp == CTRL_WARPS && lane == 0) TR(2, 2);
           for (int g = sub; g < ngroups; g += EPI_SUB) {
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   float4* px = xstate_ptr(xs, g16, j, r);
-                  const float4 xb = *px;
+                  const float4 xb = __ldcs(px);
                   const float xv[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -478,7 +481,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     const float nv = fmaf(-c12, fast_tanh(h[4 * j + e]), xv[e]);
                     xn[4 * j + e] = (valid && f < P.L) ? nv : 0.0f;
                   }
-                  *px = make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]);
+                  __stcs(px, make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
                 }
                 if (step > 1) {
                   const uint32_t keep = keep_mask16(step - 1, g16);
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     (f0 + 16 <= ld.n_valid)) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
-                    reinterpret_cast<float4*>(orow + f0)[j] = make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                    __stcs(reinterpret_cast<float4*>(orow + f0) + j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
                 } else {
 #pragma unroll
                   for (int e = 0; e < 16; ++e)
@@ -559,9 +562,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
         }
       };
+      int cur = 0;
       for (int i = T_tile; i >= 1; --i)
-        for (int l = 0; l < P.n_step; ++l) run(P.step[l], i, l, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1));
-      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l, l == P.n_dec - 1);
+        for (int l = 0; l < P.n_step; ++l) {
+          run(P.step[l], i, l, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2);   // x0 lo -> buffer 2
+          cur ^= 1;
+        }
+      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo);
     }
   }
 

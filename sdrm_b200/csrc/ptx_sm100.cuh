@@ -50,6 +50,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #ifndef SDRM_WATCHDOG_NS
 #define SDRM_WATCHDOG_NS 4000000000ull
 #endif
+// same with a sleep between polls: for the many warps that wait microseconds (epilogue warps on the accumulator), so
+// that their polling does not burn issue slots and power the tensor pipe could use under the board power cap
+__device__ __forceinline__ void mbar_wait_sleepy(uint32_t bar, uint32_t parity, int* err_word, int code, uint32_t sleep_ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(sleep_ns);
+    if (++spins == (1u << 22)) {
+      if (err_word) atomicCAS(err_word, 0, code);
+      __threadfence_system();
+      __trap();
+    }
+  }
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_word, int code) {
   // Fast path: plain polling (try_wait itself suspends the thread for a bounded time).  No timer is touched until
   // the wait has lasted implausibly long: %globaltimer / clock reads on the hot path cost far more than the poll.

@@ -79,7 +79,7 @@ def dp_train_step(stepper, optimizer, mu_global, t_global=None, group=None, inj_
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     lo, hi = shard_bounds(mu_global.shape[0], rank, world)
-    stepper.group = group if world > 1 else None
+    stepper.group = (group if group is not None else dist.group.WORLD) if world > 1 else None
     stepper.row_offset = lo
     optimizer.zero_grad()
     loss = stepper.loss(mu_global[lo:hi], None if t_global is None else t_global[lo:hi],

@@ -52,7 +52,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -72,7 +72,12 @@ def _worker(rank, world, port, q):
         # sharded "sampling" with a fake sampler: every rank returns its global row ids -> gather is the identity
         fake = lambda n, *a, row_offset=0, **k: torch.arange(row_offset, row_offset + n, dtype=torch.float32)[:, None].repeat(1, 3)
         rows, span = sdd.sample_ddpm_sharded(11, None, None, 0, seed=0, gather=True, sampler=fake)
-        q.put((rank, float(loss), grads, rows, span))
+        torch.save((rank, float(loss), grads, rows, span), os.path.join(out_dir, f"rank{rank}.pt"))
+    except Exception:
+        import traceback
+        with open(os.path.join(out_dir, f"rank{rank}.err"), "w") as fh:
+            fh.write(traceback.format_exc())
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -80,16 +85,19 @@ def _worker(rank, world, port, q):
 @pytest.mark.timeout(120)
 def test_dp_step_equals_single_process_reference():
     world = 2
+    import tempfile
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    out_dir = tempfile.mkdtemp(prefix="sdrm_dp_")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out_dir)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=100) for _ in range(world)]
     for p in procs:
-        p.join(30)
-        assert p.exitcode == 0
+        p.join(100)
+    for r, p in enumerate(procs):
+        err = os.path.join(out_dir, f"rank{r}.err")
+        assert p.exitcode == 0, open(err).read() if os.path.exists(err) else f"rank {r} exit code {p.exitcode}"
+    res = [torch.load(os.path.join(out_dir, f"rank{r}.pt"), weights_only=False) for r in range(world)]
     g = load_golden("t_nh2_T7_L24")
     for rank, loss, grads, rows, span in res:
         # the loss and EVERY gradient equal the reference's single-process step on the whole minibatch

@@ -1,0 +1,93 @@
+"""GPU parity of K3 (warp top-k, Recall/NDCG counters) against the oracle: indices and Recall bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sdrm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _scores(rows, items, seed, dtype=np.float32, ties=False):
+    rng = np.random.RandomState(seed)
+    x = rng.randn(rows, items).astype(dtype)
+    if ties:
+        x = np.round(x * 4) / 4          # heavy ties
+    return x
+
+
+@pytest.mark.parametrize("rows,items", [(95, 1008), (136, 729), (64, 3125), (40, 8582), (3, 20000), (1, 1), (7, 33)])
+@pytest.mark.parametrize("k", [1, 3, 5, 10, 20, 50, 64])
+def test_topk_indices_bit_exact(rows, items, k):
+    from sdrm_b200 import metrics
+    if k > items:
+        pytest.skip("k > items")
+    x = _scores(rows, items, seed=rows + k)
+    idx, vals = metrics.topk_device(torch.from_numpy(x).cuda(), k, return_values=True)
+    ref = orc.topk_oracle(x, k)
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    assert np.array_equal(vals.cpu().numpy(), np.take_along_axis(x, ref, axis=1))
+
+
+def test_topk_ties_neg_inf_nan_and_strided_rows():
+    from sdrm_b200 import metrics
+    x = _scores(50, 400, seed=1, ties=True)
+    x[:, 5:60] = -np.inf            # masked training items (utilities.mask_training_examples)
+    x[3, :] = -np.inf               # a fully masked row: lowest indices win
+    x[4, 7] = np.nan
+    x[5, :] = 1.0                   # all equal
+    big = torch.full((50, 512), 9.0)
+    big[:, :400] = torch.from_numpy(x)
+    view = big.cuda()[:, :400]      # row stride 512 != 400
+    for k in (1, 10, 50):
+        assert np.array_equal(metrics.topk_device(view, k).cpu().numpy(), orc.topk_oracle(x, k))
+
+
+def test_topk_float64_scores():
+    from sdrm_b200 import metrics
+    x = _scores(20, 1008, seed=3, dtype=np.float64)
+    x[:, 100] = x[:, 200] + 1e-12   # distinguishable only in float64
+    got = metrics.topk_device(torch.from_numpy(x).cuda(), 10).cpu().numpy()
+    order = np.argsort(-x, axis=1, kind="stable")[:, :10]
+    assert np.array_equal(got, order)
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 10, 20, 50])
+def test_recall_ndcg_match_reference_formulas(k):
+    """recall_at_k_batch / NDCG_binary_at_k_batch with the reference's numpy formulas (utilities.py:123-171)."""
+    from scipy.sparse import csr_matrix
+    from sdrm_b200 import metrics
+    rng = np.random.RandomState(k)
+    x = rng.randn(120, 700).astype(np.float32)
+    held = (rng.rand(120, 700) < 0.02).astype(np.float64)
+    held[0] = 0                                            # 0 relevant items -> NaN like the reference
+    seen = rng.rand(120, 700) < 0.05
+    x[seen] = -np.inf
+    rec = metrics.recall_at_k_batch(x, csr_matrix(held), k=k)
+    ndcg = metrics.NDCG_binary_at_k_batch(x, csr_matrix(held), k=k)
+    # reference formulas with np.argpartition (ties are measure-zero for continuous scores)
+    part = np.argpartition(-x, k, axis=1)[:, :k]
+    pb = np.zeros_like(x, dtype=bool)
+    pb[np.arange(120)[:, None], part] = True
+    tb = held > 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ref_rec = np.logical_and(tb, pb).sum(axis=1).astype(np.float32) / np.minimum(k, tb.sum(axis=1))
+    assert rec.dtype == ref_rec.dtype
+    assert np.array_equal(np.isnan(rec), np.isnan(ref_rec))
+    assert np.array_equal(rec[~np.isnan(rec)], ref_rec[~np.isnan(ref_rec)])        # bit-exact
+    assert np.allclose(ndcg[~np.isnan(ndcg)], orc.ndcg_at_k_oracle(x, held, k)[~np.isnan(ndcg)], rtol=1e-12, atol=0)
+    assert np.array_equal(rec[~np.isnan(rec)], orc.recall_at_k_oracle(x, held, k)[~np.isnan(rec)])
+
+
+def test_topk_full_scale_properties():
+    """BASELINE-sized rows (20 000 items): size-independent properties instead of an O(n log n) CPU check."""
+    from sdrm_b200 import metrics
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(4096, 20000, device="cuda", generator=g)
+    idx, vals = metrics.topk_device(x, 50, return_values=True)
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())                       # sorted
+    assert bool((torch.gather(x, 1, idx.long()) == vals).all())            # indices point at the values
+    kth = vals[:, -1:]
+    assert bool(((x > kth).sum(dim=1) == 49).all())                        # exactly k-1 elements beat the k-th
+    torch_idx = torch.topk(x, 50, dim=1).indices
+    assert bool((torch.sort(torch_idx, dim=1).values == torch.sort(idx.long(), dim=1).values).all())

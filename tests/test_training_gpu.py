@@ -1,0 +1,99 @@
+"""GPU parity of K2 (fused noising / loss statistics / gradient seeds) against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import TRAIN_GOLDENS, load_golden
+from helpers import modules_from_golden
+from oracle import philox_ref
+from oracle import sdrm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", TRAIN_GOLDENS)
+def test_training_step_matches_reference_golden(name):
+    """Same weights, same noise / t / dropout masks the reference drew -> same loss and same gradients."""
+    from sdrm_b200.training import DiffusionTrainStep
+    g = load_golden(name)
+    diff, _ = modules_from_golden(g, "cuda")
+    diff.train()
+    _, _, ab_t = orc.make_schedule(g["T"])
+    stepper = DiffusionTrainStep(diff, ab_t.cuda(), g["T"], g["nd"], seed=1)
+    diff.zero_grad()
+    loss = stepper.loss(g["mu"].cuda(), g["t"].cuda(), inj_noise=g["noise"].cuda().contiguous(),
+                        inj_masks=g["keeps"].cuda().contiguous())
+    loss.backward()
+    ref = g["loss_ref"].item()
+    assert abs(loss.item() - ref) <= 2e-5 * max(1.0, abs(ref)), (loss.item(), ref)
+    for k, p in diff.named_parameters():
+        gref = g["grads_ref"][k]
+        scale = gref.abs().max().item() + 1e-12
+        assert (p.grad.cpu() - gref).abs().max().item() <= 2e-4 * scale, k   # TF32-free fp32 GEMMs on the GPU vs CPU
+
+
+def test_noise_inputs_philox_stream_matches_restatement():
+    from sdrm_b200.training import CudaLossBackend
+    be = CudaLossBackend()
+    B, L, T, nd, seed, off = 300, 150, 43, 0.2, 987654321, 5000
+    mu = torch.randn(B, L, device="cuda")
+    t = torch.randint(1, T + 1, (B,), device="cuda")
+    _, _, ab_t = orc.make_schedule(T)
+    noise, in_pert, in_clean, in_shift, masks = be.noise_inputs(mu, t, ab_t.cuda(), nd, 0.1, seed, off, want_masks=True)
+    rows = np.arange(off, off + B)
+    z = philox_ref.normals(seed, philox_ref.STREAM_TRAIN_NOISE, rows, 0, L) * np.float32(nd)
+    assert np.allclose(noise.cpu().numpy(), z, rtol=2e-5, atol=2e-6)
+    for k in range(3):
+        assert np.array_equal(masks[k].cpu().numpy(), philox_ref.keep_masks(seed, philox_ref.STREAM_TRAIN_MASK, rows, k, L))
+    x_t = orc.perturb_input(mu.cpu(), t.cpu(), noise.cpu(), ab_t)
+    keep = masks.cpu().float()
+    assert torch.allclose(in_pert.cpu(), x_t * keep[0] * 2, atol=1e-6)
+    assert torch.allclose(in_clean.cpu(), mu.cpu() * keep[1] * 2, atol=1e-6)
+    assert torch.allclose(in_shift.cpu(), (mu.cpu() + 0.1 * noise.cpu()) * keep[2] * 2, atol=1e-6)
+    assert abs(masks.float().mean().item() - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("B,L", [(17, 20), (550, 830), (4096, 950)])
+def test_loss_stats_and_seeds_vs_oracle(B, L):
+    from sdrm_b200.training import CudaLossBackend
+    be = CudaLossBackend()
+    g = torch.Generator(device="cuda").manual_seed(B)
+    pred, sx, psx, mu = (torch.randn(B, L, device="cuda", generator=g) * s for s in (0.5, 0.5, 0.5, 1.0))
+    st = be.stats(pred, sx, psx, mu, 0.1)
+    r = (pred - mu).double()
+    assert abs(st[0].item() - r.sum().item()) <= 1e-6 * r.abs().sum().item()
+    assert abs(st[4].item() - B * L) == 0
+    g_pred, g_sx, g_psx, loss = be.seeds(pred, sx, psx, mu, 0.1, st)
+    o_pred, o_sx, o_psx, o_loss = orc.loss_grad_seeds(pred.cpu(), sx.cpu(), psx.cpu(), mu.cpu())
+    assert abs(loss.item() - float(o_loss)) <= 1e-5 * abs(float(o_loss))
+    for a, b in ((g_pred, o_pred), (g_sx, o_sx), (g_psx, o_psx)):
+        assert (a.cpu().double() - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+
+
+def test_three_adam_steps_track_the_oracle():
+    """A few full optimisation steps (forward, fused loss, backward, Adam) stay on the oracle's trajectory."""
+    from sdrm_b200.training import DiffusionTrainStep
+    g = load_golden("t_nh2_T7_L24")
+    diff, _ = modules_from_golden(g, "cuda")
+    ref_mod, _ = modules_from_golden(g, "cpu")
+    diff.train(); ref_mod.train()
+    _, _, ab_t = orc.make_schedule(g["T"])
+    stepper = DiffusionTrainStep(diff, ab_t.cuda(), g["T"], g["nd"], seed=3)
+    opt = torch.optim.Adam(diff.parameters(), lr=1e-3, weight_decay=1e-4, eps=1e-8)
+    opt_ref = torch.optim.Adam(ref_mod.parameters(), lr=1e-3, weight_decay=1e-4, eps=1e-8)
+    gen = torch.Generator().manual_seed(0)
+    for step in range(3):
+        noise = torch.randn(g["mu"].shape, generator=gen) * g["nd"]
+        t = torch.randint(1, g["T"] + 1, (g["mu"].shape[0],), generator=gen)
+        keeps = (torch.rand((3,) + tuple(g["mu"].shape), generator=gen) < 0.5).to(torch.uint8)
+        opt.zero_grad()
+        loss = stepper.loss(g["mu"].cuda(), t.cuda(), inj_noise=noise.cuda(), inj_masks=keeps.cuda())
+        loss.backward(); opt.step()
+        opt_ref.zero_grad()
+        sd = dict(ref_mod.named_parameters())
+        full = {k: v for k, v in ref_mod.state_dict(keep_vars=True).items()}
+        loss_ref, _ = orc.training_loss(full, g["mu"], t, noise, keeps, g["T"])
+        loss_ref.backward(); opt_ref.step()
+        assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
+    for (k, p), (_, q) in zip(diff.named_parameters(), ref_mod.named_parameters()):
+        assert torch.allclose(p.detach().cpu(), q.detach(), rtol=2e-3, atol=2e-5), k

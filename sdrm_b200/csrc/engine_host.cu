@@ -236,6 +236,55 @@ static int max_resident_ctas(int cluster, int num_sms) {
   return n * cluster;
 }
 
+// ---- TMA tensor maps (pair mode): a blob of `rows` x 128 bytes, box = `box_rows` rows, no swizzle (the images are
+// pre-swizzled in global memory), so a box lands in shared memory byte-for-byte like the bulk copies of single mode
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+static int make_rows_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return sdrm_fail(SDRM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t dims[2] = {128, rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {128, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (%d) rows=%llu box=%u", static_cast<int>(r), rows, box_rows);
+    return sdrm_fail(SDRM_ERR_CUDA, msg);
+  }
+  return SDRM_OK;
+}
+static int fill_pair_maps(ChainParams& P, size_t workspace_bytes) {
+  auto w_rows = [](const LayerDesc& d) {
+    return static_cast<unsigned long long>(d.passes == 3 ? 2 : 1) * d.NCH * d.KB * d.NC;
+  };
+  for (int l = 0; l < P.n_step; ++l) {
+    int rc = make_rows_map(&P.tm_step_w[l], P.step[l].w_img, w_rows(P.step[l]), P.step[l].NC / 2);
+    if (rc) return rc;
+  }
+  for (int l = 0; l < P.n_dec; ++l) {
+    int rc = make_rows_map(&P.tm_dec_w[l], P.dec[l].w_img, w_rows(P.dec[l]), P.dec[l].NC / 2);
+    if (rc) return rc;
+  }
+  return make_rows_map(&P.tm_act, P.scratch, workspace_bytes / 128, TILE_M);
+}
+
 static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st) {
   if (cluster == 1) {
     sdrm_layer_engine_kernel<false><<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
@@ -466,6 +515,10 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   }
   if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
   h->last_cluster = cluster;
+  if (cluster == 2) {
+    rc = fill_pair_maps(P, static_cast<size_t>(grid) * stride);
+    if (rc) return rc;
+  }
   rc = launch_engine(P, launch_grid, cluster, st);
   if (rc) return rc;
   h->last_launches = 1;

@@ -1,5 +1,6 @@
 // Shared definitions of the streaming tcgen05 layer engine (kernel K1).
 #pragma once
+#include <cuda.h>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -20,7 +21,7 @@ constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quart
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int CTRL_WARPS = 3;                      // warp0 weight producer, warp1 UMMA issuer, warp2 activation producer
 constexpr int ENGINE_THREADS = CTRL_WARPS * 32 + EPI_THREADS;
-constexpr int ENGINE_SMEM_BYTES = NUM_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 512 /*barriers, scalars*/;
+constexpr int ENGINE_SMEM_BYTES = 232448;          // all 227 KB: pair mode stages 7 x 32 KB, single mode 4 x 48 KB
 
 enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
 
@@ -64,6 +65,11 @@ struct ChainParams {
   size_t scratch_stride;  // bytes per CTA
   size_t act_buf_bytes;   // bytes of one activation buffer (KBmax * A_TILE_BYTES)
   int* err_word;
+  // pair mode only: TMA tensor maps over the weight blobs (rows of 128 B, box = NC/2 rows) and over the whole
+  // activation scratch (box = 128 rows); tensor-map loads may complete on the LEADER CTA's mbarrier (.cta_group::2)
+  CUtensorMap tm_step_w[MAX_STEP_LAYERS];
+  CUtensorMap tm_dec_w[2];
+  CUtensorMap tm_act;
   int debug_flags;            // perf experiments only: 1 = skip activation stores, 2 = skip fp32 state traffic, 4 = skip noise
   unsigned long long* trace;  // debug: [3 roles][TRACE_CAP] (event code << 56 | globaltimer ns), CTA 0 only; or nullptr
 };

@@ -47,16 +47,16 @@ __device__ __forceinline__ float4* xstate_ptr(float* xs, int g16, int j, int r) 
 // PAIR = false: one CTA per row tile, tcgen05 cta_group::1, 4 stages of (A 16 KB + W 32 KB).
 // PAIR = true : two CTAs (a thread-block cluster of 2 = one TPC) work as a tcgen05 cta_group::2 pair on TWO row tiles
 //               (UMMA M = 256): each CTA stages its own A tile and only HALF of every weight k-block, so a stage is
-//               32 KB and 6 of them fit -> 50 % more k-blocks in flight per SM, and half the weight bytes per SM.
+//               32 KB and 7 of them fit -> 75 % more k-blocks in flight per SM, and half the weight bytes per SM.
 //               The L2 round trip under load (~1.5 us) times the bytes per k-block is what bounds this kernel
 //               (Little's law on 192 KB of staging), which is why the pair mode is the fast path.
 template <bool PAIR>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
-  constexpr int NSTG = PAIR ? 6 : 4;
+  constexpr int NSTG = PAIR ? 7 : 4;
   constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = PAIR ? 2 : 1;
-  static_assert(NSTG * STG_BYTES == NUM_STAGES * STAGE_BYTES, "both modes use the same staging footprint");
+  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 5 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -132,97 +132,100 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 
   if (warp == 0 || warp == 2) {
     // ============================ TMA producers: warp 0 streams weights, warp 2 streams activations =========
-    // Two issuing threads halve the per-k-block issue latency of the ring; the weight stream does not depend on the
-    // previous layer's epilogue, so it runs ahead across layer boundaries.
-    if (lane == 0) {
-      const bool is_w = (warp == 0);
-      uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier
-      for (int it = 0; it < n_iters; ++it) {
-        const long long tile = tile_of(it);
-        if (!PAIR && tile >= n_tiles) break;
-        int T_tile = P.T;
-        if (!is_w || !PAIR) {   // (single mode: T_tile may be per tile)
-          mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
-          T_tile = tile_T[it & 1];
-        }
-        const uint8_t* sc = scratch_of(tile);
-        // Readiness of this layer's input is tracked per CHUNK of the producing layer (one act_ready phase per chunk
-        // epilogue): k-block kb only needs the chunks covering features < 64 (kb + 1), so the next layer starts while the
-        // previous layer's last chunk is still in its epilogue.
-        int prev_nch = 0, prev_nc = 1;
-        auto run = [&](const LayerDesc& ld, int in_hi_buf, int in_lo_buf) {
-          int ready = 0;
-          if (!is_w) TR(0, 1);
-          const uint8_t* a_hi = sc + static_cast<size_t>(in_hi_buf) * P.act_buf_bytes;
-          const uint8_t* a_lo = sc + static_cast<size_t>(in_lo_buf) * P.act_buf_bytes;
-          const uint32_t w_bytes = static_cast<uint32_t>(ld.NC) * 128u;       // one whole weight k-block image
-          const uint32_t w_mine = PAIR ? w_bytes / 2 : w_bytes;               // the N-half this CTA feeds to the pair UMMA
-          const uint32_t w_off = PAIR ? cta_rank * w_mine : 0u;
-          for (int c = 0; c < ld.NCH; ++c) {
-            for (int p = 0; p < ld.passes; ++p) {
-              const uint8_t* a_src = (p == 2) ? a_lo : a_hi;
-              const int which = (p == 1) ? 1 : 0;
-              const uint8_t* w_src = ld.w_img + (static_cast<size_t>(which) * ld.NCH + c) * ld.KB * w_bytes + w_off;
-              for (int kb = 0; kb < ld.KB; ++kb) {
-                mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
-                const uint32_t fb = bar_full(stage);
-                if (is_w) {
-                  mbar_arrive_expect_tx(fb, w_mine);
-                  bulk_g2s(stage_w(stage), w_src, w_mine, fb);
-                  w_src += w_bytes;
-                } else {
-                  if (c == 0 && p == 0) {
-                    int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
-                    if (need > prev_nch || kb == ld.KB - 1) need = prev_nch;
-                    while (ready < need) {
-                      mbar_wait(bar_act_chunk(ready), (act_par >> ready) & 1u, err, WD_PRODUCER_ACT);
-                      act_par ^= (1u << ready);
-                      ++ready;
-                    }
-                    if (kb == 0) TR(0, 2);
+    // The whole warp runs the loops CONVERGED and one elected lane issues the copies: single-lane (divergent) code makes
+    // the compiler wrap every uniform-datapath instruction (UBLKCP / UTMALDG / UTCHMMA) in an elect loop and costs
+    // ~0.5 us per k-block.  The weight stream does not depend on the previous layer's epilogue and runs ahead.
+    const bool is_w = (warp == 0);
+    uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier
+    for (int it = 0; it < n_iters; ++it) {
+      const long long tile = tile_of(it);
+      if (!PAIR && tile >= n_tiles) break;
+      int T_tile = P.T;
+      if (!is_w || !PAIR) {   // (single mode: T_tile may be per tile)
+        mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
+        T_tile = tile_T[it & 1];
+      }
+      const uint8_t* sc = scratch_of(tile);
+      const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
+      // Readiness of a layer's input is tracked per CHUNK of the producing layer (one barrier per chunk index): k-block
+      // kb only needs the chunks covering features < 64 (kb + 1), so a layer starts while the previous layer's last
+      // chunk is still in its epilogue.
+      int prev_nch = 0, prev_nc = 1;
+      auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf) {
+        const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes, kind = ldref.kind;
+        const uint8_t* w_img = ldref.w_img;
+        int ready = 0;
+        if (!is_w) TR(0, 1);
+        const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
+        const int half_rows = NC >> 1;
+        for (int c = 0; c < NCH; ++c) {
+          for (int p = 0; p < passes; ++p) {
+            const int which = (p == 1) ? 1 : 0;
+            const int a_buf = (p == 2) ? in_lo_buf : in_hi_buf;
+            const uint8_t* a_src = sc + static_cast<size_t>(a_buf) * P.act_buf_bytes;
+            const uint8_t* w_src = w_img + (static_cast<size_t>(which) * NCH + c) * KB * w_bytes;
+            int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank) * half_rows;
+            int a_row = a_row_base + static_cast<int>((static_cast<size_t>(a_buf) * P.act_buf_bytes) >> 7);
+            for (int kb = 0; kb < KB; ++kb) {
+              if (!is_w && c == 0 && p == 0) {
+                int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
+                if (need > prev_nch || kb == KB - 1) need = prev_nch;
+                while (ready < need) {
+                  mbar_wait(bar_act_chunk(ready), (act_par >> ready) & 1u, err, WD_PRODUCER_ACT);
+                  act_par ^= (1u << ready);
+                  ++ready;
+                }
+                if (kb == 0) TR(0, 2);
+              }
+              mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
+              const uint32_t fb = bar_full(stage);
+              if (elect_one()) {
+                if (PAIR) {
+                  // both CTAs load into their own stage but complete on the LEADER's full barrier; the leader's two
+                  // producers arm it with the bytes of both CTAs
+                  const uint32_t fb0 = mapa_cluster(fb, 0);
+                  if (is_w) {
+                    if (cta_rank == 0) mbar_arrive_expect_tx(fb, w_bytes);
+                    tma_load_2d_pair(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0);
+                  } else {
+                    if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2 * A_TILE_BYTES);
+                    tma_load_2d_pair(mapa_cluster(stage_a(stage), cta_rank), &P.tm_act, 0, a_row, fb0);
                   }
-                  TR(0, 4);
+                } else if (is_w) {
+                  mbar_arrive_expect_tx(fb, w_bytes);
+                  bulk_g2s(stage_w(stage), w_src, w_bytes, fb);
+                } else {
                   mbar_arrive_expect_tx(fb, A_TILE_BYTES);
                   bulk_g2s(stage_a(stage), a_src, A_TILE_BYTES, fb);
-                  a_src += A_TILE_BYTES;
-                  TR(0, 5);
-                  ++trace_seq;
                 }
-                if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
+              __syncwarp();
+              w_row += NC;
+              a_row += A_TILE_BYTES >> 7;
+              w_src += w_bytes;
+              a_src += A_TILE_BYTES;
+              if (!is_w) { TR(0, 5); ++trace_seq; }
+              if (++stage == NSTG) { stage = 0; sphase ^= 1; }
             }
-            if (!is_w) TR(0, 3);
           }
-          prev_nch = (ld.kind == EPI_LINEAR_OUT) ? 0 : ld.NCH;
-          prev_nc = ld.NC;
-        };
-        // chain layers ping-pong between activation buffers 0 and 1 (in = parity of the layer count so far); only two
-        // hot buffers per CTA keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
-        int cur = 0;
-        for (int i = T_tile; i >= 1; --i)
-          for (int l = 0; l < P.n_step; ++l) { run(P.step[l], cur, cur); cur ^= 1; }
-        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
-      }
+          if (!is_w) TR(0, 3);
+        }
+        prev_nch = (kind == EPI_LINEAR_OUT) ? 0 : NCH;
+        prev_nc = NC;
+      };
+      // chain layers ping-pong between activation buffers 0 and 1 (in = parity of the layer count so far); only two
+      // hot buffers per CTA keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
+      int cur = 0;
+      for (int i = T_tile; i >= 1; --i)
+        for (int l = 0; l < P.n_step; ++l) { run(P.step[l], &P.tm_step_w[l], cur, cur); cur ^= 1; }
+      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
     }
   } else if (warp == 1) {
     if (PAIR && cta_rank != 0) {
-      // ============================== peer CTA: relay "my stage is full" to the leader ==============
-      // One lane per stage: a remote release-arrive costs most of a microsecond, so the six stages are relayed by
-      // six independent lanes instead of one serial loop.
-      if (lane == 0) {
-        long long kb_per_step = 0, kb_dec = 0;
-        for (int l = 0; l < P.n_step; ++l) kb_per_step += static_cast<long long>(P.step[l].NCH) * P.step[l].passes * P.step[l].KB;
-        for (int l = 0; l < P.n_dec; ++l) kb_dec += static_cast<long long>(P.dec[l].NCH) * P.dec[l].passes * P.dec[l].KB;
-        const long long total = static_cast<long long>(n_iters) * (kb_per_step * P.T + kb_dec);
-        uint32_t stage = 0, ph = 0;
-        for (long long i = 0; i < total; ++i) {
-          mbar_wait(bar_full(stage), ph, err, WD_MMA_FULL);
-          mbar_arrive_cluster(mapa_cluster(bar_peer_full(stage), 0));
-          if (++stage == NSTG) { stage = 0; ph ^= 1; }
-        }
-      }
-    } else if (lane == 0) {
+      // peer CTA of a pair: the leader issues every UMMA; the peer's TMA loads complete on the leader's barriers
+    } else {
       // ======================================= UMMA issuer ========================================
+      // whole warp converged, one elected lane issues (see the producer comment)
       uint32_t stage = 0, sphase = 0, cc = 0;
       for (int it = 0; it < n_iters; ++it) {
         if (!PAIR && tile_of(it) >= n_tiles) break;
@@ -231,9 +234,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait(bar_tile_ready, it & 1, err, WD_MMA_TILE);
           T_tile = tile_T[it & 1];
         }
-        auto run = [&](const LayerDesc& ld) {
-          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ld.NC);
-          for (int c = 0; c < ld.NCH; ++c) {
+        auto run = [&](const LayerDesc& ldref) {
+          const int KB = ldref.KB, NCH = ldref.NCH, passes = ldref.passes, kmma_last = ldref.kmma_last;
+          const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ldref.NC);
+          for (int c = 0; c < NCH; ++c) {
             const uint32_t buf = cc & 1u;
             TR(1, 1);
             mbar_wait(bar_acc_empty(buf), ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
@@ -241,30 +245,42 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             TR(1, 2);
             const uint32_t d_tmem = tmem_base + buf * 256u;
             uint32_t acc = 0;
-            for (int p = 0; p < ld.passes; ++p) {
-              for (int kb = 0; kb < ld.KB; ++kb) {
+            for (int p = 0; p < passes; ++p) {
+              for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
-                if (PAIR) { TR(1, 7); mbar_wait(bar_peer_full(stage), sphase, err, WD_MMA_FULL); }
                 tc_fence_after();
                 TR(1, kb == 0 && p == 0 ? 3 : 5);
                 const uint64_t a_desc = umma_desc_sw128(stage_a(stage));
                 const uint64_t b_desc = umma_desc_sw128(stage_w(stage));
-                const int nk = (kb == ld.KB - 1) ? ld.kmma_last : 4;
-                for (int k = 0; k < nk; ++k) {
+                const int nk = (kb == KB - 1) ? kmma_last : 4;
+                if (elect_one()) {
                   // +32 B (16 bf16) along K inside the swizzle row = +2 in the 16-byte address field
-                  if (PAIR) umma_bf16_ss_pair(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
-                  else umma_bf16_ss(d_tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, acc);
-                  acc = 1;
+                  if (PAIR) {
+                    umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, acc);
+                    if (nk > 1) umma_bf16_ss_pair(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
+                    if (nk > 2) umma_bf16_ss_pair(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
+                    if (nk > 3) umma_bf16_ss_pair(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
+                    umma_commit_pair(bar_empty(stage), 0x3);
+                  } else {
+                    umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc);
+                    if (nk > 1) umma_bf16_ss(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
+                    if (nk > 2) umma_bf16_ss(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
+                    if (nk > 3) umma_bf16_ss(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
+                    umma_commit(bar_empty(stage));
+                  }
                 }
-                if (PAIR) umma_commit_pair(bar_empty(stage), 0x3);
-                else umma_commit(bar_empty(stage));
+                __syncwarp();
+                acc = 1;
                 TR(1, 6);
                 ++trace_seq;
                 if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
             }
-            if (PAIR) umma_commit_pair(bar_acc_full(buf), 0x3);
-            else umma_commit(bar_acc_full(buf));
+            if (elect_one()) {
+              if (PAIR) umma_commit_pair(bar_acc_full(buf), 0x3);
+              else umma_commit(bar_acc_full(buf));
+            }
+            __syncwarp();
             TR(1, 4);
             ++cc;
           }

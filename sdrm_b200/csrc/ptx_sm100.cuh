@@ -40,6 +40,18 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
       : "memory");
   return ok;
 }
+// one lane of a converged warp (uniform-datapath instructions should be issued under this predicate)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -101,6 +113,17 @@ __device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
       ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
       : "memory");
+}
+// 2-D tensor-map load whose destination is this CTA's shared memory but whose completion is signalled on the mbarrier of
+// either CTA of the tcgen05 pair (both addresses are shared::cluster addresses, see mapa_cluster)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_cluster, const void* tmap, int c0, int c1, uint32_t bar_cluster) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_cluster), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, uint32_t src_smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"

@@ -8,6 +8,7 @@ from sdrm_b200.train_SDRM import sample_ddpm, engine_for
 w = dict(WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg5"]); w["T"] = 4
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 18944
 lib = _lib.load(); lib.sdrm_set_cluster_override(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+lib.sdrm_debug_set_flags(int(os.environ.get('SDRM_DEBUG_FLAGS', '0')))
 diff, vae = build_models(w, "cuda")
 CAP = 8192
 buf = torch.zeros(3 * CAP, dtype=torch.int64, device="cuda")

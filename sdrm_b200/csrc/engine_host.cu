@@ -502,8 +502,9 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
-  // the cta_group::2 pair mode (full-resolution chains only) is opt-in via sdrm_set_cluster_override(2): with the
-  // relay-based stage hand-off it is still ~4 % slower than single-CTA mode on B200 (kernel K1)
+  // full-resolution chains run on tcgen05 cta_group::2 CTA pairs (fewer weight bytes and more k-blocks in flight per SM);
+  // multi-resolution chains (per-tile step counts) and single-tile calls use single-CTA mode
+  if (d_t_start == nullptr && n_tiles >= 2) cluster = 2;
   if (g_cluster_override > 0 && (d_t_start == nullptr || g_cluster_override == 1)) cluster = g_cluster_override;
   int launch_grid = 0;
   for (; cluster >= 1; cluster >>= 1) {

@@ -361,30 +361,38 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const bool active = valid && (step <= t_row);
         if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
         const float c2 = cf.y, sg = cf.z;
+        // issue the four state loads first (they stream from L2 / HBM), then generate the four Philox quads (independent
+        // chains the compiler interleaves), then update
+        float4 xo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xo[j] = __ldcs(xstate_ptr(xs, g16, j, r));   // streaming: keep the activation images in L2
+        float z[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float4* px = xstate_ptr(xs, g16, j, r);
-          const float4 xo = __ldcs(px);   // streaming: the fp32 state must not evict the activation images from L2
-          float z4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[j][e] = 0.0f;
           if (sg != 0.0f) {
             if (P.inj_z) {
               const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int f = g16 * 16 + 4 * j + e;
-                z4[e] = f < P.L ? zp[f] : 0.0f;
+                z[j][e] = f < P.L ? zp[f] : 0.0f;
               }
             } else {
-              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z4);
+              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z[j]);
             }
           }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
           float4 o;
           const int f = g16 * 16 + 4 * j;
-          o.x = (f + 0 < P.L) ? fmaf(sg, z4[0], xo.x * c2) : 0.0f;
-          o.y = (f + 1 < P.L) ? fmaf(sg, z4[1], xo.y * c2) : 0.0f;
-          o.z = (f + 2 < P.L) ? fmaf(sg, z4[2], xo.z * c2) : 0.0f;
-          o.w = (f + 3 < P.L) ? fmaf(sg, z4[3], xo.w * c2) : 0.0f;
-          __stcs(px, o);
+          o.x = (f + 0 < P.L) ? fmaf(sg, z[j][0], xo[j].x * c2) : 0.0f;
+          o.y = (f + 1 < P.L) ? fmaf(sg, z[j][1], xo[j].y * c2) : 0.0f;
+          o.z = (f + 2 < P.L) ? fmaf(sg, z[j][2], xo[j].z * c2) : 0.0f;
+          o.w = (f + 3 < P.L) ? fmaf(sg, z[j][3], xo[j].w * c2) : 0.0f;
+          __stcs(xstate_ptr(xs, g16, j, r), o);
         }
       };
 
@@ -486,18 +494,19 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const int g16 = f0 >> 4;
               if (g16 < P.Lg16) {
                 float xn[16];
+                float4 xb4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xb4[j] = __ldcs(xstate_ptr(xs, g16, j, r));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  float4* px = xstate_ptr(xs, g16, j, r);
-                  const float4 xb = __ldcs(px);
-                  const float xv[4] = {xb.x, xb.y, xb.z, xb.w};
+                  const float xv[4] = {xb4[j].x, xb4[j].y, xb4[j].z, xb4[j].w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const int f = f0 + 4 * j + e;
                     const float nv = fmaf(-c12, fast_tanh(h[4 * j + e]), xv[e]);
                     xn[4 * j + e] = (valid && f < P.L) ? nv : 0.0f;
                   }
-                  __stcs(px, make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
+                  __stcs(xstate_ptr(xs, g16, j, r), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
                 }
                 if (step > 1) {
                   const uint32_t keep = keep_mask16(step - 1, g16);
@@ -562,13 +571,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           if (warp == CTRL_WARPS && lane == 0) TR(2, 3);
           ++cc;
-          if (!last_of_tile && ld.kind != EPI_LINEAR_OUT) {
-            // this chunk's activations are complete: publish them to the TMA (async) proxy and tell the A producer
+          // Publish this chunk's activations to the TMA (async) proxy and tell the A producer.  The proxy fence has to
+          // drain the thread's stores (~1 us): the LAST chunk of a layer publishes at once (the next layer's tail k-blocks
+          // wait for it), earlier chunks publish after their noise slice, when the stores have long landed.
+          const bool publishes = !last_of_tile && ld.kind != EPI_LINEAR_OUT;
+          auto publish = [&]() {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act_chunk(c));
             if (warp == CTRL_WARPS && lane == 0) TR(2, 5);
-          }
+          };
+          if (publishes && c == ld.NCH - 1) publish();
           // spare time while the tensor core works on the next chunk: a slice of this step's noise
           if (ld.kind == EPI_PRELU && noise_slots > 0) {
             const int todo = (noise_total - noise_done + noise_slots - 1) / noise_slots;
@@ -576,6 +589,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             --noise_slots;
             if (warp == CTRL_WARPS && lane == 0) TR(2, 4);
           }
+          if (publishes && c != ld.NCH - 1) publish();
         }
       };
       int cur = 0;

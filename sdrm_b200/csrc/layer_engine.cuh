@@ -20,14 +20,15 @@ constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
 constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int CTRL_WARPS = 3;                      // warp0 weight producer, warp1 UMMA issuer, warp2 activation producer
-constexpr int ENGINE_THREADS = CTRL_WARPS * 32 + EPI_THREADS;
+constexpr int NOISE_WARPS = 4;                     // one thread per tile row: Gaussian half of the posterior update
+constexpr int ENGINE_THREADS = CTRL_WARPS * 32 + EPI_THREADS + NOISE_WARPS * 32;
 constexpr int ENGINE_SMEM_BYTES = 232448;          // all 227 KB: pair mode stages 7 x 32 KB, single mode 4 x 48 KB
 
 enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
 
 // error codes the device watchdog writes (which wait timed out)
 enum : int { WD_PRODUCER_EMPTY = 101, WD_PRODUCER_ACT = 102, WD_PRODUCER_TILE = 103, WD_MMA_FULL = 201,
-             WD_MMA_ACC = 202, WD_MMA_TILE = 203, WD_EPI_ACC = 301 };
+             WD_MMA_ACC = 202, WD_MMA_TILE = 203, WD_EPI_ACC = 301, WD_EPI_NOISE = 302, WD_NOISE_STATE = 401, WD_NOISE_TILE = 402 };
 
 struct LayerDesc {
   const uint8_t* w_img;   // weight images [which: hi, lo][chunk][k block][NC rows x 128 B], 128B-swizzled

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = PAIR ? 2 : 1;
-  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 5 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
+  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -76,7 +76,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // one barrier per chunk INDEX: chunk c of layer l+1 cannot finish before the A producer consumed chunk c of layer l,
   // so a waiter never lags more than one phase (a single barrier would be lapped by fast chunk epilogues)
   auto bar_act_chunk = [&](uint32_t c) { return bar_base + 8u * (3 * NSTG + 5 + c); };
-  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 5 + MAX_ACT_CHUNKS);
+  const uint32_t bar_state_ready = bar_base + 8u * (3 * NSTG + 5 + MAX_ACT_CHUNKS);      // epilogue -> noise warps
+  const uint32_t bar_noise_ready = bar_base + 8u * (3 * NSTG + 6 + MAX_ACT_CHUNKS);      // noise warps -> epilogue
+  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS);
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
@@ -96,6 +98,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_acc_empty(0), EPI_WARPS * NCTA);   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
     mbar_init(bar_acc_empty(1), EPI_WARPS * NCTA);
     for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(c), EPI_WARPS);
+    mbar_init(bar_state_ready, EPI_WARPS);
+    mbar_init(bar_noise_ready, NOISE_WARPS);
     mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
       }
     }
-  } else {
+  } else if (warp < CTRL_WARPS + EPI_WARPS) {
     // ======================================= epilogue warps =====================================
     // 16 warps: warp (q, sub) reads TMEM lane quarter q (rows 32q..32q+31) and owns the 16-column groups
     // g = sub (mod 4).  One thread always touches the same (row, columns) of the fp32 state, so the state
@@ -309,11 +313,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (size_t i = threadIdx.x - CTRL_WARPS * 32; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       epi_bar_sync();
     }
-    // noise groups of this thread per step: g = sub, sub + 4, ... < Lg16
-    const int noise_total = (P.Lg16 > sub) ? (P.Lg16 - sub + EPI_SUB - 1) / EPI_SUB : 0;
-    int noise_slots_per_step = 0;
-    for (int l = 0; l + 1 < P.n_step; ++l) noise_slots_per_step += P.step[l].NCH;
-
+    uint32_t noise_par = 0;
     for (; it < n_iters; ++it) {
       const long long tile = tile_of(it);
       if (!PAIR && tile >= n_tiles) break;
@@ -353,49 +353,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         return philox_mask16(P.seed, STREAM_MASK, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16));
       };
 
-      // Noise half of the posterior update, done AHEAD of the eps GEMM of the same step (z does not depend on the
-      // network): state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
-      auto noise_group = [&](int step, int g16) {
-        if (P.debug_flags & 4) return;
-        const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
-        const bool active = valid && (step <= t_row);
-        if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
-        const float c2 = cf.y, sg = cf.z;
-        // issue the four state loads first (they stream from L2 / HBM), then generate the four Philox quads (independent
-        // chains the compiler interleaves), then update
-        float4 xo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xo[j] = __ldcs(xstate_ptr(xs, g16, j, r));   // streaming: keep the activation images in L2
-        float z[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) z[j][e] = 0.0f;
-          if (sg != 0.0f) {
-            if (P.inj_z) {
-              const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int f = g16 * 16 + 4 * j + e;
-                z[j][e] = f < P.L ? zp[f] : 0.0f;
-              }
-            } else {
-              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z[j]);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 o;
-          const int f = g16 * 16 + 4 * j;
-          o.x = (f + 0 < P.L) ? fmaf(sg, z[j][0], xo[j].x * c2) : 0.0f;
-          o.y = (f + 1 < P.L) ? fmaf(sg, z[j][1], xo[j].y * c2) : 0.0f;
-          o.z = (f + 2 < P.L) ? fmaf(sg, z[j][2], xo[j].z * c2) : 0.0f;
-          o.w = (f + 3 < P.L) ? fmaf(sg, z[j][3], xo[j].w * c2) : 0.0f;
-          __stcs(xstate_ptr(xs, g16, j, r), o);
-        }
-      };
-
       // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38); also the noise half of the first step
       if (P.n_step > 0) {
         uint8_t* in0 = sc;   // the first chain layer reads activation buffer 0
@@ -429,16 +386,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             pk[e] = pack_bf16x2(a0, a1);
           }
           store_act16(in0, r, g * 16, pk);
-          noise_group(T_tile, g);
         }
       }
       if (warp == CTRL_WARPS && lane == 0) tile_T[it & 1] = T_tile;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tile_ready);
-
-      int noise_done = noise_total;   // the tile's first step got its noise in the init above
-      int noise_slots = 0;
 
       // ---- layers
       auto run = [&](const LayerDesc& ld, int step, int layer_idx, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
@@ -451,16 +404,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         if (ld.kind == EPI_POSTERIOR) {
           const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
           c12 = active ? cf.x * cf.y : 0.0f;
-          while (noise_done < noise_total) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
-        } else if (step >= 1 && layer_idx == 0 && step != T_tile) {
-          noise_done = 0;
-          noise_slots = noise_slots_per_step;
+          // the noise warps have turned the state into x_i / sqrt(a_i) + sqrt(b_i) nd z_i for this step
+          mbar_wait_sleepy(bar_noise_ready, noise_par, err, WD_EPI_NOISE, 128);
+          noise_par ^= 1;
         }
         const int ngroups = ld.NC >> 4;
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
           if (warp == CTRL_WARPS && lane == 0) TR(2, 1);
-          mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 256);
+          mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           if (warp == CTRL_WARPS && lane == 0) TR(2, 2);
           for (int g = sub; g < ngroups; g += EPI_SUB) {
@@ -481,11 +433,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             }
             if (ld.kind == EPI_PRELU) {
               uint32_t pk[8];
+              if (slope >= 0.0f && slope <= 1.0f) {
+                // PReLU(h) = max(h, a h) for 0 <= a <= 1 (every trained SDRM slope; init 0.25): FMUL + FMNMX per element
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float a0 = h[2 * e] > 0.f ? h[2 * e] : slope * h[2 * e];
-                const float a1 = h[2 * e + 1] > 0.f ? h[2 * e + 1] : slope * h[2 * e + 1];
-                pk[e] = pack_bf16x2(a0, a1);
+                for (int e = 0; e < 8; ++e)
+                  pk[e] = pack_bf16x2(fmaxf(h[2 * e], slope * h[2 * e]), fmaxf(h[2 * e + 1], slope * h[2 * e + 1]));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const float a0 = h[2 * e] > 0.f ? h[2 * e] : slope * h[2 * e];
+                  const float a1 = h[2 * e + 1] > 0.f ? h[2 * e + 1] : slope * h[2 * e + 1];
+                  pk[e] = pack_bf16x2(a0, a1);
+                }
               }
               store_act16(out_hi, r, f0, pk, P.debug_flags & 1);
             } else if (ld.kind == EPI_POSTERIOR) {
@@ -571,9 +530,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           if (warp == CTRL_WARPS && lane == 0) TR(2, 3);
           ++cc;
-          // Publish this chunk's activations to the TMA (async) proxy and tell the A producer.  The proxy fence has to
-          // drain the thread's stores (~1 us): the LAST chunk of a layer publishes at once (the next layer's tail k-blocks
-          // wait for it), earlier chunks publish after their noise slice, when the stores have long landed.
+          // publish this chunk's activations to the TMA (async) proxy and tell the A producer
           const bool publishes = !last_of_tile && ld.kind != EPI_LINEAR_OUT;
           auto publish = [&]() {
             fence_proxy_async();
@@ -581,15 +538,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             if (lane == 0) mbar_arrive(bar_act_chunk(c));
             if (warp == CTRL_WARPS && lane == 0) TR(2, 5);
           };
-          if (publishes && c == ld.NCH - 1) publish();
-          // spare time while the tensor core works on the next chunk: a slice of this step's noise
-          if (ld.kind == EPI_PRELU && noise_slots > 0) {
-            const int todo = (noise_total - noise_done + noise_slots - 1) / noise_slots;
-            for (int k = 0; k < todo; ++k) { noise_group(step, sub + EPI_SUB * noise_done); ++noise_done; }
-            --noise_slots;
-            if (warp == CTRL_WARPS && lane == 0) TR(2, 4);
-          }
-          if (publishes && c != ld.NCH - 1) publish();
+          if (publishes) publish();
+        }
+        if (ld.kind == EPI_POSTERIOR && step > 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_state_ready);   // x_{i-1} is complete: the noise warps may prepare step i-1
         }
       };
       int cur = 0;
@@ -599,6 +552,78 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           cur ^= 1;
         }
       for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo);
+    }
+  } else {
+    // ======================================= noise warps ========================================
+    // Thread r owns tile row r.  For every step i it turns the fp32 state x_i into x_i / sqrt(a_i) + sqrt(b_i) nd z_i
+    // (the part of the DDPM posterior that does not depend on the network) while the tensor core and the epilogue warps
+    // run the step's dense layers; z comes from the Philox stream keyed by (global row, step, column).
+    const int r = (warp - CTRL_WARPS - EPI_WARPS) * 32 + lane;
+    uint32_t st_par = 0;
+    for (int it = 0; it < n_iters; ++it) {
+      const long long tile = tile_of(it);
+      if (!PAIR && tile >= n_tiles) break;
+      uint8_t* sc = scratch_of(tile);
+      float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+      const long long prow = tile * TILE_M + r;
+      const bool valid = prow < P.n_rows;
+      const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;
+      const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
+      int t_row = P.T;
+      if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
+      mbar_wait_sleepy(bar_tile_ready, it & 1, err, WD_NOISE_TILE, 128);   // x_T is in place
+      const int T_tile = (P.n_step == 0) ? 0 : tile_T[it & 1];
+      // Noise half of the posterior update, done AHEAD of the eps GEMM of the same step (z does not depend on the
+      // network): state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
+      auto noise_group = [&](int step, int g16) {
+        if (P.debug_flags & 4) return;
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
+        const bool active = valid && (step <= t_row);
+        if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
+        const float c2 = cf.y, sg = cf.z;
+        // issue the four state loads first (they stream from L2 / HBM), then generate the four Philox quads (independent
+        // chains the compiler interleaves), then update
+        float4 xo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xo[j] = __ldcs(xstate_ptr(xs, g16, j, r));   // streaming: keep the activation images in L2
+        float z[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) z[j][e] = 0.0f;
+          if (sg != 0.0f) {
+            if (P.inj_z) {
+              const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int f = g16 * 16 + 4 * j + e;
+                z[j][e] = f < P.L ? zp[f] : 0.0f;
+              }
+            } else {
+              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 o;
+          const int f = g16 * 16 + 4 * j;
+          o.x = (f + 0 < P.L) ? fmaf(sg, z[j][0], xo[j].x * c2) : 0.0f;
+          o.y = (f + 1 < P.L) ? fmaf(sg, z[j][1], xo[j].y * c2) : 0.0f;
+          o.z = (f + 2 < P.L) ? fmaf(sg, z[j][2], xo[j].z * c2) : 0.0f;
+          o.w = (f + 3 < P.L) ? fmaf(sg, z[j][3], xo[j].w * c2) : 0.0f;
+          __stcs(xstate_ptr(xs, g16, j, r), o);
+        }
+      };
+      for (int i = T_tile; i >= 1; --i) {
+        if (i != T_tile) {
+          mbar_wait_sleepy(bar_state_ready, st_par, err, WD_NOISE_STATE, 128);
+          st_par ^= 1;
+        }
+        for (int g = 0; g < P.Lg16; ++g) noise_group(i, g);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_noise_ready);
+      }
     }
   }
 

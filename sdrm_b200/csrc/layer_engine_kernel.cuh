@@ -30,16 +30,40 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8], bool skip = false) {
   if (skip) return;
   const int kb = f0 >> 6;
-  const int j0 = (f0 & 63) >> 3;
-  uint8_t* base = buf + static_cast<size_t>(kb) * A_TILE_BYTES + r * 128;
+  const int j0 = (f0 & 63) >> 3;   // even: the two 16-byte pieces share one aligned 32-byte sector of the swizzled row
   const int sw = r & 7;
-  *reinterpret_cast<uint4*>(base + ((j0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  *reinterpret_cast<uint4*>(base + (((j0 + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  uint8_t* sector = buf + static_cast<size_t>(kb) * A_TILE_BYTES + r * 128 + (((j0 ^ sw) & ~1) << 4);
+  const bool flip = sw & 1;        // odd rows hold the pair in swapped order (128-byte swizzle XOR)
+  const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
+  const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
+  // one 256-bit store (STG.256): the stores scatter over 32 rows per warp, so halving their count halves the L1 cost
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3)
+               : "memory");
 }
 
-// fp32 state layout inside a tile: [16-col group][float4 index 0..3][row 0..127][4 floats]
-__device__ __forceinline__ float4* xstate_ptr(float* xs, int g16, int j, int r) {
-  return reinterpret_cast<float4*>(xs) + (static_cast<size_t>(g16) * 4 + j) * TILE_M + r;
+// fp32 state layout inside a tile: [16-col group][half 0..1][row 0..127][8 floats]; a thread moves its 16 columns with two
+// 256-bit streaming accesses (evict-first: the state must not push the activation images out of L2), a warp touches
+// 1 KB contiguous per access
+__device__ __forceinline__ float* xstate_ptr8(float* xs, int g16, int half, int r) {
+  return xs + ((static_cast<size_t>(g16) * 2 + half) * TILE_M + r) * 8;
+}
+__device__ __forceinline__ void xs_load16(float* xs, int g16, int r, float (&x)[16]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf)
+    asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(x[8 * hf + 0]), "=f"(x[8 * hf + 1]), "=f"(x[8 * hf + 2]), "=f"(x[8 * hf + 3]), "=f"(x[8 * hf + 4]),
+                   "=f"(x[8 * hf + 5]), "=f"(x[8 * hf + 6]), "=f"(x[8 * hf + 7])
+                 : "l"(xstate_ptr8(xs, g16, hf, r))
+                 : "memory");
+}
+__device__ __forceinline__ void xs_store16(float* xs, int g16, int r, const float (&x)[16]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf)
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(xstate_ptr8(xs, g16, hf, r)), "f"(x[8 * hf + 0]), "f"(x[8 * hf + 1]), "f"(x[8 * hf + 2]), "f"(x[8 * hf + 3]),
+                   "f"(x[8 * hf + 4]), "f"(x[8 * hf + 5]), "f"(x[8 * hf + 6]), "f"(x[8 * hf + 7])
+                 : "memory");
 }
 
 }  // namespace
@@ -375,8 +399,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const int f = g * 16 + j * 4 + e;
               x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;
             }
-            __stcs(xstate_ptr(xs, g, j, r), make_float4(x[j * 4], x[j * 4 + 1], x[j * 4 + 2], x[j * 4 + 3]));
           }
+          xs_store16(xs, g, r, x);
           const uint32_t keep = keep_mask16(T_tile, g);
           uint32_t pk[8];
 #pragma unroll
@@ -453,20 +477,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const int g16 = f0 >> 4;
               if (g16 < P.Lg16) {
                 float xn[16];
-                float4 xb4[4];
+                xs_load16(xs, g16, r, xn);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xb4[j] = __ldcs(xstate_ptr(xs, g16, j, r));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float xv[4] = {xb4[j].x, xb4[j].y, xb4[j].z, xb4[j].w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const int f = f0 + 4 * j + e;
-                    const float nv = fmaf(-c12, fast_tanh(h[4 * j + e]), xv[e]);
-                    xn[4 * j + e] = (valid && f < P.L) ? nv : 0.0f;
-                  }
-                  __stcs(xstate_ptr(xs, g16, j, r), make_float4(xn[4 * j], xn[4 * j + 1], xn[4 * j + 2], xn[4 * j + 3]));
+                for (int e = 0; e < 16; ++e) {
+                  const float nv = fmaf(-c12, fast_tanh(h[e]), xn[e]);
+                  xn[e] = (valid && f0 + e < P.L) ? nv : 0.0f;
                 }
+                xs_store16(xs, g16, r, xn);
                 if (step > 1) {
                   const uint32_t keep = keep_mask16(step - 1, g16);
                   uint32_t pk[8];
@@ -583,9 +600,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const float c2 = cf.y, sg = cf.z;
         // issue the four state loads first (they stream from L2 / HBM), then generate the four Philox quads (independent
         // chains the compiler interleaves), then update
-        float4 xo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) xo[j] = __ldcs(xstate_ptr(xs, g16, j, r));   // streaming: keep the activation images in L2
+        float xo[16];
+        xs_load16(xs, g16, r, xo);
         float z[4][4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -605,15 +621,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4 o;
-          const int f = g16 * 16 + 4 * j;
-          o.x = (f + 0 < P.L) ? fmaf(sg, z[j][0], xo[j].x * c2) : 0.0f;
-          o.y = (f + 1 < P.L) ? fmaf(sg, z[j][1], xo[j].y * c2) : 0.0f;
-          o.z = (f + 2 < P.L) ? fmaf(sg, z[j][2], xo[j].z * c2) : 0.0f;
-          o.w = (f + 3 < P.L) ? fmaf(sg, z[j][3], xo[j].w * c2) : 0.0f;
-          __stcs(xstate_ptr(xs, g16, j, r), o);
-        }
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int f = g16 * 16 + 4 * j + e;
+            xo[4 * j + e] = (f < P.L) ? fmaf(sg, z[j][e], xo[4 * j + e] * c2) : 0.0f;
+          }
+        xs_store16(xs, g16, r, xo);
       };
       for (int i = T_tile; i >= 1; --i) {
         if (i != T_tile) {

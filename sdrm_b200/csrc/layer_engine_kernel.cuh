@@ -10,8 +10,8 @@
 //   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
 //     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the
 //     bf16 (or bf16 hi/lo) re-quantisation, and write the next layer's A images (L2-resident scratch);
-//   * warp 0 = weight TMA producer, warp 1 = UMMA issuer (one elected thread), warp 2 = activation TMA producer,
-//     warps 3-18 = epilogue; the epilogue
+//   * warps 0-15 = epilogue, 16-19 = noise, 20 = weight TMA producer, 21 = UMMA issuer, 22 = activation TMA producer;
+//     the epilogue
 //     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
 // Rows are independent, so there is no inter-CTA synchronisation anywhere.
 #pragma once
@@ -27,7 +27,7 @@ namespace {
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // write 16 consecutive bf16 features [f0, f0+16) of tile row r into a k-block image buffer
-__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8], bool skip = false) {
+__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8], uint64_t pol, bool skip = false) {
   if (skip) return;
   const int kb = f0 >> 6;
   const int j0 = (f0 & 63) >> 3;   // even: the two 16-byte pieces share one aligned 32-byte sector of the swizzled row
@@ -37,8 +37,8 @@ __device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const u
   const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
   const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
   // one 256-bit store (STG.256): the stores scatter over 32 rows per warp, so halving their count halves the L1 cost
-  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3)
+  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+               ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol)
                : "memory");
 }
 
@@ -87,13 +87,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t base_addr = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base_addr - raw_addr);
   const uint32_t bar_base = base_addr + NSTG * STG_BYTES;
-  // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | peer_full[NSTG] | acc_full[2] | acc_empty[2] | tile_ready |
+  // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | (unused NSTG) | acc_full[2] | acc_empty[2] | tile_ready |
   //                             act_chunk[MAX_ACT_CHUNKS]
   auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
   auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
   auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
   auto bar_empty = [&](uint32_t s) { return bar_base + 8u * (NSTG + s); };
-  auto bar_peer_full = [&](uint32_t s) { return bar_base + 8u * (2 * NSTG + s); };
   auto bar_acc_full = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + b); };
   auto bar_acc_empty = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + 2 + b); };
   const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 4);
@@ -111,11 +110,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_WARP && lane == 0) {
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(bar_full(s), 2);     // weight producer + activation producer each arm their own byte count
       mbar_init(bar_empty(s), 1);
-      mbar_init(bar_peer_full(s), 1);
     }
     mbar_init(bar_acc_full(0), 1);
     mbar_init(bar_acc_full(1), 1);
@@ -127,7 +125,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == M_WARP) {
     if (PAIR) { tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish_pair(); }
     else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
   }
@@ -145,7 +143,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   auto tile_of = [&](int it) -> long long { return (static_cast<long long>(it) * n_clusters + my_cluster) * NCTA + cta_rank; };
   int* err = P.err_word;
   int trace_n = 0;
-  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp >= CTRL_WARPS);
+  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp < W_WARP);
   unsigned long long trace_seq = 0;  // k-block sequence number of the role (for matching producer / consumer events)
   const bool trace_kb = (P.debug_flags & 8) != 0;   // per-k-block events perturb the pipeline; off by default
   auto TR = [&](int role, unsigned long long code) {
@@ -158,12 +156,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
   };
 
-  if (warp == 0 || warp == 2) {
+  if (warp == W_WARP || warp == A_WARP) {
     // ============================ TMA producers: warp 0 streams weights, warp 2 streams activations =========
     // The whole warp runs the loops CONVERGED and one elected lane issues the copies: single-lane (divergent) code makes
     // the compiler wrap every uniform-datapath instruction (UBLKCP / UTMALDG / UTCHMMA) in an elect loop and costs
     // ~0.5 us per k-block.  The weight stream does not depend on the previous layer's epilogue and runs ahead.
-    const bool is_w = (warp == 0);
+    const bool is_w = (warp == W_WARP);
+    const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier
     for (int it = 0; it < n_iters; ++it) {
       const long long tile = tile_of(it);
@@ -214,17 +213,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   const uint32_t fb0 = mapa_cluster(fb, 0);
                   if (is_w) {
                     if (cta_rank == 0) mbar_arrive_expect_tx(fb, w_bytes);
-                    tma_load_2d_pair(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0);
+                    tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
                   } else {
                     if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2 * A_TILE_BYTES);
-                    tma_load_2d_pair(mapa_cluster(stage_a(stage), cta_rank), &P.tm_act, 0, a_row, fb0);
+                    tma_load_2d_pair_hint(mapa_cluster(stage_a(stage), cta_rank), &P.tm_act, 0, a_row, fb0, pol_keep);
                   }
                 } else if (is_w) {
                   mbar_arrive_expect_tx(fb, w_bytes);
-                  bulk_g2s(stage_w(stage), w_src, w_bytes, fb);
+                  bulk_g2s_hint(stage_w(stage), w_src, w_bytes, fb, pol_keep);
                 } else {
                   mbar_arrive_expect_tx(fb, A_TILE_BYTES);
-                  bulk_g2s(stage_a(stage), a_src, A_TILE_BYTES, fb);
+                  bulk_g2s_hint(stage_a(stage), a_src, A_TILE_BYTES, fb, pol_keep);
                 }
               }
               __syncwarp();
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         for (int l = 0; l < P.n_step; ++l) { run(P.step[l], &P.tm_step_w[l], cur, cur); cur ^= 1; }
       for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
     }
-  } else if (warp == 1) {
+  } else if (warp == M_WARP) {
     if (PAIR && cta_rank != 0) {
       // peer CTA of a pair: the leader issues every UMMA; the peer's TMA loads complete on the leader's barriers
     } else {
@@ -318,13 +317,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
       }
     }
-  } else if (warp < CTRL_WARPS + EPI_WARPS) {
+  } else if (warp < EPI_WARPS) {
     // ======================================= epilogue warps =====================================
     // 16 warps: warp (q, sub) reads TMEM lane quarter q (rows 32q..32q+31) and owns the 16-column groups
     // g = sub (mod 4).  One thread always touches the same (row, columns) of the fp32 state, so the state
     // needs no synchronisation at all.
+    const uint64_t pol_keep = l2_policy_evict_last();
     const int q = warp & 3;
-    const int sub = (warp - CTRL_WARPS) >> 2;
+    const int sub = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t cc = 0;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     if (!P.preloaded_input) {
       uint4* z = reinterpret_cast<uint4*>(scratch_of(blockIdx.x));
       const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
-      for (size_t i = threadIdx.x - CTRL_WARPS * 32; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (size_t i = threadIdx.x; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       epi_bar_sync();
     }
     uint32_t noise_par = 0;
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       int m = t_row;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-      if (lane == 0) warp_max[(it & 1) * EPI_WARPS + (warp - CTRL_WARPS)] = m;
+      if (lane == 0) warp_max[(it & 1) * EPI_WARPS + warp] = m;
       epi_bar_sync();
       int T_tile = 0;
 #pragma unroll
@@ -409,10 +409,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * x[2 * e + 1] : 0.0f;
             pk[e] = pack_bf16x2(a0, a1);
           }
-          store_act16(in0, r, g * 16, pk);
+          store_act16(in0, r, g * 16, pk, pol_keep);
         }
       }
-      if (warp == CTRL_WARPS && lane == 0) tile_T[it & 1] = T_tile;
+      if (warp == 0 && lane == 0) tile_T[it & 1] = T_tile;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tile_ready);
@@ -435,10 +435,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int ngroups = ld.NC >> 4;
         for (int c = 0; c < ld.NCH; ++c) {
           const uint32_t buf = cc & 1u;
-          if (warp == CTRL_WARPS && lane == 0) TR(2, 1);
+          if (warp == 0 && lane == 0) TR(2, 1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
-          if (warp == CTRL_WARPS && lane == 0) TR(2, 2);
+          if (warp == 0 && lane == 0) TR(2, 2);
           for (int g = sub; g < ngroups; g += EPI_SUB) {
             uint32_t v[16];
             tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   pk[e] = pack_bf16x2(a0, a1);
                 }
               }
-              store_act16(out_hi, r, f0, pk, P.debug_flags & 1);
+              store_act16(out_hi, r, f0, pk, pol_keep, P.debug_flags & 1);
             } else if (ld.kind == EPI_POSTERIOR) {
               // x_{i-1} = (x_i - eps (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) nd z; the state already holds
               // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise_group), so only the eps term is left.
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * xn[2 * e + 1] : 0.0f;
                     pk[e] = pack_bf16x2(a0, a1);
                   }
-                  store_act16(out_hi, r, f0, pk);
+                  store_act16(out_hi, r, f0, pk, pol_keep);
                 } else {
                   // last reverse step: hand x_0 to the decoder as bf16 hi/lo (bf16x3 GEMM)
                   uint32_t ph[8], pl[8];
@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     ph[e] = pack_bf16x2(h0, h1);
                     pl[e] = pack_bf16x2(xn[2 * e] - h0, xn[2 * e + 1] - h1);
                   }
-                  store_act16(out_hi, r, f0, ph);
-                  store_act16(out_lo, r, f0, pl);
+                  store_act16(out_hi, r, f0, ph, pol_keep);
+                  store_act16(out_lo, r, f0, pl, pol_keep);
                   if (P.x0_out && valid) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
@@ -521,8 +521,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 ph[e] = pack_bf16x2(h0, h1);
                 pl[e] = pack_bf16x2(t0 - h0, t1 - h1);
               }
-              store_act16(out_hi, r, f0, ph);
-              store_act16(out_lo, r, f0, pl);
+              store_act16(out_hi, r, f0, ph, pol_keep);
+              store_act16(out_lo, r, f0, pl, pol_keep);
             } else {  // EPI_LINEAR_OUT
               if (valid) {
                 float* orow = P.logits + static_cast<size_t>(row) * P.ld_logits;
@@ -545,7 +545,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), 0));   // the leader CTA issues the UMMAs
             else mbar_arrive(bar_acc_empty(buf));
           }
-          if (warp == CTRL_WARPS && lane == 0) TR(2, 3);
+          if (warp == 0 && lane == 0) TR(2, 3);
           ++cc;
           // publish this chunk's activations to the TMA (async) proxy and tell the A producer
           const bool publishes = !last_of_tile && ld.kind != EPI_LINEAR_OUT;
@@ -553,7 +553,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act_chunk(c));
-            if (warp == CTRL_WARPS && lane == 0) TR(2, 5);
+            if (warp == 0 && lane == 0) TR(2, 5);
           };
           if (publishes) publish();
         }
@@ -575,7 +575,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // Thread r owns tile row r.  For every step i it turns the fp32 state x_i into x_i / sqrt(a_i) + sqrt(b_i) nd z_i
     // (the part of the DDPM posterior that does not depend on the network) while the tensor core and the epilogue warps
     // run the step's dense layers; z comes from the Philox stream keyed by (global row, step, column).
-    const int r = (warp - CTRL_WARPS - EPI_WARPS) * 32 + lane;
+    const int r = (warp - NOISE_WARP0) * 32 + lane;
     uint32_t st_par = 0;
     for (int it = 0; it < n_iters; ++it) {
       const long long tile = tile_of(it);
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   tc_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its operands
-  if (warp == 1) {
+  if (warp == M_WARP) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, 512);
     else tmem_dealloc(tmem_base, 512);

@@ -99,27 +99,34 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
 // ----------------------------------------------------------------------------------------------
 // TMA bulk engine (1-D bulk copy global -> shared, completion on an mbarrier)
 // ----------------------------------------------------------------------------------------------
+// L2 eviction-priority policies: the activation images and weights are re-read within microseconds (evict_last), the
+// fp32 state and the logits stream through (evict_first / .cs)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// 2-D tensor-map load whose destination is this CTA's shared memory but whose completion is signalled on the mbarrier of
+// either CTA of the tcgen05 pair (both addresses are shared::cluster addresses, see mapa_cluster)
+__device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_cluster, const void* tmap, int c0, int c1, uint32_t bar_cluster,
+                                                      uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst_cluster), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster), "l"(pol)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion on a local mbarrier (plain form: used by the microbenchmarks in tools/)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
       ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar)
       : "memory");
 }
-// same, multicast: the bytes land at the same CTA-relative offset in every CTA of `cta_mask`, and complete_tx is
-// signalled on the mbarrier at the same offset in each of them
-__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar,
-                                                   uint16_t cta_mask) {
+// same with an L2 eviction-priority hint (single-CTA mode of the engine)
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar, uint64_t pol) {
   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
-      ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
-      : "memory");
-}
-// 2-D tensor-map load whose destination is this CTA's shared memory but whose completion is signalled on the mbarrier of
-// either CTA of the tcgen05 pair (both addresses are shared::cluster addresses, see mapa_cluster)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_cluster, const void* tmap, int c0, int c1, uint32_t bar_cluster) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%2, %3}], [%4];"
-      ::"r"(dst_cluster), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
@@ -229,11 +236,6 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // default semantics (.release at CTA scope) like CUTLASS ClusterBarrier::arrive(cta_id): a cluster-scope release would
   // first drain every outstanding global store of the thread (measured: ~10 us per epilogue chunk)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(cta_mask)
-               : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

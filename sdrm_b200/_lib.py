@@ -30,6 +30,7 @@ SIGNATURES = {
     "sdrm_debug_set_trace": (None, [_P]),
     "sdrm_debug_set_flags": (None, [C.c_int]),
     "sdrm_last_cluster_size": (C.c_int, [_P]),
+    "sdrm_resident_ctas": (C.c_int, [_P, C.c_int]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "sdrm_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),
     "sdrm_topk_f64": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),

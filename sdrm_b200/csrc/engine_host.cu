@@ -173,7 +173,7 @@ struct sdrm_handle {
   int num_sms = 0;
   int last_launches = 0;
   int last_cluster = 1;
-  int resident[5] = {0, 0, 0, 0, 0};  // resident CTAs per cluster size
+  int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per cluster size (1, 2, 4, 8)
   int* err_word = nullptr;
   // denoiser
   bool have_den = false;
@@ -213,8 +213,10 @@ static int engine_set_smem_attr() {
   int dev = 0;
   SDRM_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && done[dev]) return SDRM_OK;
-  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
-  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return SDRM_OK;
 }
@@ -231,7 +233,9 @@ static int max_resident_ctas(int cluster, int num_sms) {
   attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   int n = 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<true>, &cfg);
+  cudaError_t e = cluster == 2   ? cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<2>, &cfg)
+                  : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<4>, &cfg)
+                                 : cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<8>, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n * cluster;
 }
@@ -270,16 +274,16 @@ static int make_rows_map(CUtensorMap* map, const void* base, unsigned long long 
   }
   return SDRM_OK;
 }
-static int fill_pair_maps(ChainParams& P, size_t workspace_bytes) {
+static int fill_pair_maps(ChainParams& P, size_t workspace_bytes, int cluster) {
   auto w_rows = [](const LayerDesc& d) {
     return static_cast<unsigned long long>(d.passes == 3 ? 2 : 1) * d.NCH * d.KB * d.NC;
   };
   for (int l = 0; l < P.n_step; ++l) {
-    int rc = make_rows_map(&P.tm_step_w[l], P.step[l].w_img, w_rows(P.step[l]), P.step[l].NC / 2);
+    int rc = make_rows_map(&P.tm_step_w[l], P.step[l].w_img, w_rows(P.step[l]), P.step[l].NC / cluster);
     if (rc) return rc;
   }
   for (int l = 0; l < P.n_dec; ++l) {
-    int rc = make_rows_map(&P.tm_dec_w[l], P.dec[l].w_img, w_rows(P.dec[l]), P.dec[l].NC / 2);
+    int rc = make_rows_map(&P.tm_dec_w[l], P.dec[l].w_img, w_rows(P.dec[l]), P.dec[l].NC / cluster);
     if (rc) return rc;
   }
   return make_rows_map(&P.tm_act, P.scratch, workspace_bytes / 128, TILE_M);
@@ -287,7 +291,7 @@ static int fill_pair_maps(ChainParams& P, size_t workspace_bytes) {
 
 static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st) {
   if (cluster == 1) {
-    sdrm_layer_engine_kernel<false><<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
+    sdrm_layer_engine_kernel<1><<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
     SDRM_CUDA(cudaGetLastError());
     return SDRM_OK;
   }
@@ -300,7 +304,10 @@ static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<true>, P));
+  if (cluster == 2) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<2>, P));
+  else if (cluster == 4) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<4>, P));
+  else if (cluster == 8) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<8>, P));
+  else return sdrm_fail(SDRM_ERR_BAD_ARG, "launch_engine: cluster size");
   return SDRM_OK;
 }
 
@@ -334,6 +341,8 @@ int sdrm_create(sdrm_handle** out, int device) {
   if (engine_set_smem_attr() != SDRM_OK) { delete h; return SDRM_ERR_CUDA; }
   h->resident[1] = h->num_sms;
   h->resident[2] = max_resident_ctas(2, h->num_sms);
+  h->resident[4] = max_resident_ctas(4, h->num_sms);
+  h->resident[8] = max_resident_ctas(8, h->num_sms);
   *out = h;
   return SDRM_OK;
 }
@@ -433,7 +442,7 @@ static int kb_max_of(const sdrm_handle* h) {
 static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* act_bytes, size_t* stride) {
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   // upper bound over every cluster choice (a cluster launch rounds the grid up to a multiple of the cluster size)
-  *grid = static_cast<int>(std::max<long long>(4, std::min<long long>((n_tiles + 3) / 4 * 4, (h->num_sms + 3) / 4 * 4)));
+  *grid = static_cast<int>(std::max<long long>(8, std::min<long long>((n_tiles + 7) / 8 * 8, (h->num_sms + 7) / 8 * 8)));
   *act_bytes = static_cast<size_t>(kb_max_of(h)) * A_TILE_BYTES;
   const int Lg16 = (h->L + 15) / 16;
   const size_t xs = static_cast<size_t>(Lg16) * 4 * TILE_M * 16;
@@ -516,8 +525,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   }
   if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
   h->last_cluster = cluster;
-  if (cluster == 2) {
-    rc = fill_pair_maps(P, static_cast<size_t>(grid) * stride);
+  if (cluster >= 2) {
+    rc = fill_pair_maps(P, static_cast<size_t>(grid) * stride, cluster);
     if (rc) return rc;
   }
   rc = launch_engine(P, launch_grid, cluster, st);
@@ -559,7 +568,8 @@ static int g_probe_repeat = 1;
 void sdrm_probe_set_repeat(int n) { g_probe_repeat = n < 1 ? 1 : n; }
 void sdrm_debug_set_flags(int f) { g_debug_flags = f; }
 void sdrm_debug_set_trace(void* d_buf) { g_trace = static_cast<unsigned long long*>(d_buf); }
-void sdrm_set_cluster_override(int c) { g_cluster_override = (c == 1 || c == 2) ? c : 0; }
+void sdrm_set_cluster_override(int c) { g_cluster_override = (c == 1 || c == 2 || c == 4 || c == 8) ? c : 0; }
+int sdrm_resident_ctas(const sdrm_handle* h, int cluster) { return (h && cluster >= 1 && cluster <= 8) ? h->resident[cluster] : 0; }
 int sdrm_last_cluster_size(const sdrm_handle* h) { return h ? h->last_cluster : 0; }
 
 size_t sdrm_probe_linear_workspace_bytes(int64_t M, int K, int N) {

@@ -74,12 +74,18 @@ __device__ __forceinline__ void xs_store16(float* xs, int g16, int r, const floa
 //               32 KB and 7 of them fit -> 75 % more k-blocks in flight per SM, and half the weight bytes per SM.
 //               The L2 round trip under load (~1.5 us) times the bytes per k-block is what bounds this kernel
 //               (Little's law on 192 KB of staging), which is why the pair mode is the fast path.
-template <bool PAIR>
+//               CS = 4 / 8: a cluster of CS/2 such pairs that run the same layer sequence in lock step and SHARE the weight
+//               stream: every CTA loads 1/CS of a weight k-block and TMA-multicasts it to the CTAs of the other pairs
+//               that hold the same N-half, so the L2 -> SM weight traffic per SM drops by CS/2.  The kernel is bound by
+//               L2 bandwidth (A re-reads + weights), not by the tensor pipe, which is why this pays.
+template <int CS>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
+  constexpr bool PAIR = CS >= 2;
+  constexpr int NPAIRS = PAIR ? CS / 2 : 1;
   constexpr int NSTG = PAIR ? 7 : 4;
   constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
-  constexpr int NCTA = PAIR ? 2 : 1;
+  constexpr int NCTA = CS;
   static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
@@ -109,16 +115,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
+  const uint32_t leader_rank = cta_rank & ~1u;   // CTA of this tcgen05 pair that issues the UMMAs and owns the barriers
+  const uint32_t pair_idx = cta_rank >> 1;
 
   if (warp == W_WARP && lane == 0) {
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(bar_full(s), 2);     // weight producer + activation producer each arm their own byte count
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_empty(s), NPAIRS);   // a stage is refilled (partly by the other pairs) once EVERY pair consumed it
     }
     mbar_init(bar_acc_full(0), 1);
     mbar_init(bar_acc_full(1), 1);
-    mbar_init(bar_acc_empty(0), EPI_WARPS * NCTA);   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
-    mbar_init(bar_acc_empty(1), EPI_WARPS * NCTA);
+    mbar_init(bar_acc_empty(0), EPI_WARPS * (PAIR ? 2 : 1));   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
+    mbar_init(bar_acc_empty(1), EPI_WARPS * (PAIR ? 2 : 1));
     for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(c), EPI_WARPS);
     mbar_init(bar_state_ready, EPI_WARPS);
     mbar_init(bar_noise_ready, NOISE_WARPS);
@@ -185,13 +193,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         if (!is_w) TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
         const int half_rows = NC >> 1;
+        const int part_rows = NC / CS;          // rows of a weight k-block this CTA fetches (CS >= 4: multicast to its peers)
         for (int c = 0; c < NCH; ++c) {
           for (int p = 0; p < passes; ++p) {
             const int which = (p == 1) ? 1 : 0;
             const int a_buf = (p == 2) ? in_lo_buf : in_hi_buf;
             const uint8_t* a_src = sc + static_cast<size_t>(a_buf) * P.act_buf_bytes;
             const uint8_t* w_src = w_img + (static_cast<size_t>(which) * NCH + c) * KB * w_bytes;
-            int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank) * half_rows;
+            int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank & 1u) * half_rows +
+                        (CS > 2 ? static_cast<int>(pair_idx) * part_rows : 0);
             int a_row = a_row_base + static_cast<int>((static_cast<size_t>(a_buf) * P.act_buf_bytes) >> 7);
             for (int kb = 0; kb < KB; ++kb) {
               if (!is_w && c == 0 && p == 0) {
@@ -210,12 +220,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 if (PAIR) {
                   // both CTAs load into their own stage but complete on the LEADER's full barrier; the leader's two
                   // producers arm it with the bytes of both CTAs
-                  const uint32_t fb0 = mapa_cluster(fb, 0);
+                  const uint32_t fb0 = mapa_cluster(fb, leader_rank);
                   if (is_w) {
-                    if (cta_rank == 0) mbar_arrive_expect_tx(fb, w_bytes);
-                    tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
+                    if (cta_rank == leader_rank) mbar_arrive_expect_tx(fb, w_bytes);
+                    if (CS > 2) {
+                      // this CTA's 1/CS of the k-block goes to the same smem offset of every CTA holding this N-half;
+                      // each copy completes on the full barrier of the destination's own pair leader
+                      constexpr uint16_t kHalfMask = static_cast<uint16_t>(CS == 8 ? 0x55u : 0x05u);
+                      tma_load_2d_pair_mcast_hint(stage_w(stage) + pair_idx * static_cast<uint32_t>(part_rows) * 128u, tm_w, 0, w_row,
+                                                  fb & 0xFEFFFFFFu, static_cast<uint16_t>(kHalfMask << (cta_rank & 1u)), pol_keep);
+                    } else {
+                      tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
+                    }
                   } else {
-                    if (cta_rank == 0) mbar_arrive_expect_tx(fb, 2 * A_TILE_BYTES);
+                    if (cta_rank == leader_rank) mbar_arrive_expect_tx(fb, 2 * A_TILE_BYTES);
                     tma_load_2d_pair_hint(mapa_cluster(stage_a(stage), cta_rank), &P.tm_act, 0, a_row, fb0, pol_keep);
                   }
                 } else if (is_w) {
@@ -248,7 +266,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
     }
   } else if (warp == M_WARP) {
-    if (PAIR && cta_rank != 0) {
+    if (PAIR && cta_rank != leader_rank) {
       // peer CTA of a pair: the leader issues every UMMA; the peer's TMA loads complete on the leader's barriers
     } else {
       // ======================================= UMMA issuer ========================================
@@ -287,7 +305,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     if (nk > 1) umma_bf16_ss_pair(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
                     if (nk > 2) umma_bf16_ss_pair(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
                     if (nk > 3) umma_bf16_ss_pair(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
-                    umma_commit_pair(bar_empty(stage), 0x3);
+                    umma_commit_pair(bar_empty(stage), static_cast<uint16_t>((1u << CS) - 1u));   // every CTA of the cluster
                   } else {
                     umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc);
                     if (nk > 1) umma_bf16_ss(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
@@ -304,7 +322,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               }
             }
             if (elect_one()) {
-              if (PAIR) umma_commit_pair(bar_acc_full(buf), 0x3);
+              if (PAIR) umma_commit_pair(bar_acc_full(buf), static_cast<uint16_t>(0x3u << leader_rank));
               else umma_commit(bar_acc_full(buf));
             }
             __syncwarp();
@@ -542,7 +560,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), 0));   // the leader CTA issues the UMMAs
+            if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), leader_rank));   // the leader CTA issues the UMMAs
             else mbar_arrive(bar_acc_empty(buf));
           }
           if (warp == 0 && lane == 0) TR(2, 3);

@@ -84,7 +84,8 @@ def test_partition_invariance():
 
 
 def test_single_and_pair_mode_are_bit_identical():
-    """The weight stream chain runs on single CTAs (cta_group::1) or CTA pairs (cta_group::2, UMMA M=256); rows do not change."""
+    """The chain runs on single CTAs (cta_group::1), CTA pairs (cta_group::2, UMMA M=256) or clusters of 2 / 4 pairs sharing
+    one multicast weight stream; rows do not change."""
     from sdrm_b200 import _lib
     lib = _lib.load()
     n, I, H, L, T, nh, nd = 1500, 700, 200, 264, 7, 2, 1.0     # 12 row tiles; ragged last tile; ghost tiles for cluster 4
@@ -92,13 +93,17 @@ def test_single_and_pair_mode_are_bit_identical():
     eng = _engine(diff, vae, T, nd)
     outs = {}
     try:
-        for c in (1, 2):
+        for c in (1, 2, 4, 8):
+            if lib.sdrm_resident_ctas(eng.handle, c) < c:
+                continue
             lib.sdrm_set_cluster_override(c)
             outs[c] = eng.sample(n, seed=77, check=True).clone()
             assert lib.sdrm_last_cluster_size(eng.handle) == c
     finally:
         lib.sdrm_set_cluster_override(0)
-    assert torch.equal(outs[1], outs[2])
+    assert 1 in outs and 2 in outs and 4 in outs
+    for c in outs:
+        assert torch.equal(outs[1], outs[c]), c
 
 
 def test_random_mode_matches_oracle():

@@ -66,6 +66,20 @@ def keep_masks(seed, stream, rows, step, n_cols):
     return bits.reshape(len(rows), ng * 16)[:, :n_cols].astype(np.uint8)
 
 
+def keep_masks128(seed, stream, rows, step, n_cols):
+    """Sampler dropout keep mask block [len(rows), n_cols] (uint8 0/1): one Philox call per 128 columns,
+    column 128*b + 32*w + j is bit j of output word w (philox_mask128 in philox.cuh)."""
+    rows = np.asarray(rows, dtype=np.uint64)
+    nb = (n_cols + 127) // 128
+    cb = np.arange(nb, dtype=np.uint32)[None, :]
+    r_lo = (rows & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
+    c3 = (np.uint32(stream) | ((rows >> np.uint64(32)).astype(np.uint32) << np.uint32(8)))[:, None]
+    words = philox4x32_10(cb, np.uint32(step), r_lo, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = np.stack(words, axis=-1)                                   # [rows, nb, 4]
+    bits = (w[..., None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)   # [rows, nb, 4, 32]
+    return bits.reshape(len(rows), nb * 128)[:, :n_cols].astype(np.uint8)
+
+
 def sampler_noise(seed, row_offset, n, L, T):
     """The exact (x_T, z[T+1], keep[T+1]) tensors sdrm_sample generates in-kernel for rows row_offset..+n."""
     rows = np.arange(row_offset, row_offset + n, dtype=np.uint64)
@@ -75,5 +89,5 @@ def sampler_noise(seed, row_offset, n, L, T):
     for i in range(1, T + 1):
         if i >= 2:
             z[i] = normals(seed, STREAM_NORMAL, rows, i, L)
-        keep[i] = keep_masks(seed, STREAM_MASK, rows, i, L)
+        keep[i] = keep_masks128(seed, STREAM_MASK, rows, i, L)
     return xT, z, keep

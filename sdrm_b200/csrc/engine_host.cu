@@ -439,14 +439,18 @@ static int kb_max_of(const sdrm_handle* h) {
   return kb;
 }
 
-static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* act_bytes, size_t* stride) {
+static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* act_bytes, size_t* stride, size_t* mask_off = nullptr,
+                            int* mask_pitch = nullptr) {
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   // upper bound over every cluster choice (a cluster launch rounds the grid up to a multiple of the cluster size)
   *grid = static_cast<int>(std::max<long long>(8, std::min<long long>((n_tiles + 7) / 8 * 8, (h->num_sms + 7) / 8 * 8)));
   *act_bytes = static_cast<size_t>(kb_max_of(h)) * A_TILE_BYTES;
   const int Lg16 = (h->L + 15) / 16;
   const size_t xs = static_cast<size_t>(Lg16) * 4 * TILE_M * 16;
-  *stride = NUM_ACT_BUFS * (*act_bytes) + xs;
+  const int pitch = 16 * ((Lg16 + 7) / 8);   // one 128-bit Philox block of keep bits per 128 columns
+  if (mask_off) *mask_off = NUM_ACT_BUFS * (*act_bytes) + xs;
+  if (mask_pitch) *mask_pitch = pitch;
+  *stride = NUM_ACT_BUFS * (*act_bytes) + xs + static_cast<size_t>(TILE_M) * pitch;
 }
 
 size_t sdrm_sample_workspace_bytes(const sdrm_handle* h, int64_t n) {
@@ -468,8 +472,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   if (!d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: null workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
-  int grid; size_t act, stride;
-  sample_geometry(h, n, &grid, &act, &stride);
+  int grid, mask_pitch; size_t act, stride, mask_off;
+  sample_geometry(h, n, &grid, &act, &stride, &mask_off, &mask_pitch);
   if (workspace_bytes < static_cast<size_t>(grid) * stride) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small");
   int rc = engine_set_smem_attr();
   if (rc) return rc;
@@ -505,6 +509,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.scratch = static_cast<uint8_t*>(d_workspace);
   P.scratch_stride = stride;
   P.act_buf_bytes = act;
+  P.mask_off = mask_off;
+  P.mask_pitch = mask_pitch;
   P.err_word = h->err_word;
   P.trace = g_trace;
   P.debug_flags = g_debug_flags;

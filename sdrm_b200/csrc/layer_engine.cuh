@@ -19,7 +19,7 @@ constexpr int MAX_ACT_CHUNKS = 8;                  // N chunks of an activation-
 constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
 constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int CTRL_WARPS = 3;                      // weight producer, UMMA issuer, activation producer
+constexpr int CTRL_WARPS = 4;                      // weight producer, UMMA issuer, activation producer (+1 idle: setmaxnreg works on whole warpgroups)
 constexpr int NOISE_WARPS = 4;                     // one thread per tile row: Gaussian half of the posterior update
 constexpr int ENGINE_THREADS = CTRL_WARPS * 32 + EPI_THREADS + NOISE_WARPS * 32;
 // warp roles: epilogue 0..15, noise 16..19, control 20..22.  The control warps get the HIGHEST warp ids: the SM's warp
@@ -28,6 +28,10 @@ constexpr int NOISE_WARP0 = EPI_WARPS;
 constexpr int W_WARP = EPI_WARPS + NOISE_WARPS;    // weight TMA producer
 constexpr int M_WARP = W_WARP + 1;                 // UMMA issuer (also allocates TMEM)
 constexpr int A_WARP = W_WARP + 2;                 // activation TMA producer
+// Register budget (setmaxnreg, per warpgroup): the kernel launches with 80 registers per thread (768 threads); the control
+// warpgroup drops to 40 and the noise warpgroup to 56 so that the four epilogue warpgroups can grow to 96.
+constexpr int REGS_CTRL = 56, REGS_NOISE = 72, REGS_EPI = 88;
+static_assert(128 * (REGS_CTRL + REGS_NOISE) + EPI_THREADS * REGS_EPI <= 80 * ENGINE_THREADS, "register pool");
 constexpr int ENGINE_SMEM_BYTES = 232448;          // all 227 KB: pair mode stages 7 x 32 KB, single mode 4 x 48 KB
 
 enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_LINEAR_OUT = 3 };
@@ -71,13 +75,15 @@ struct ChainParams {
   uint8_t* scratch;       // per-CTA (or per-tile in probe mode) scratch
   size_t scratch_stride;  // bytes per CTA
   size_t act_buf_bytes;   // bytes of one activation buffer (KBmax * A_TILE_BYTES)
+  size_t mask_off;        // per-CTA scratch: offset of the dropout keep bits [128 rows][mask_pitch bytes] (bit c of a row = column c)
+  int mask_pitch;         // bytes per row of keep bits: 16 * ceil(Lg16 / 8)
   int* err_word;
   // pair mode only: TMA tensor maps over the weight blobs (rows of 128 B, box = NC/2 rows) and over the whole
   // activation scratch (box = 128 rows); tensor-map loads may complete on the LEADER CTA's mbarrier (.cta_group::2)
   CUtensorMap tm_step_w[MAX_STEP_LAYERS];
   CUtensorMap tm_dec_w[2];
   CUtensorMap tm_act;
-  int debug_flags;            // perf experiments only: 1 = skip activation stores, 2 = skip fp32 state traffic, 4 = skip noise
+  int debug_flags;            // perf experiments only (-DSDRM_PERF_DEBUG builds): 1 = skip activation stores, 4 = skip noise; 8 = trace k-blocks
   unsigned long long* trace;  // debug: [3 roles][TRACE_CAP] (event code << 56 | globaltimer ns), CTA 0 only; or nullptr
 };
 constexpr int TRACE_CAP = 8192;

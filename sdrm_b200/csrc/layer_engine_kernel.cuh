@@ -19,28 +19,33 @@
 #include "philox.cuh"
 #include "ptx_sm100.cuh"
 
+#include <type_traits>
+
+// Event-timeline tracing (tools/trace_timeline.py) and the perf-experiment switches cost instructions in the hottest
+// loops of a kernel that is bound by issue slots: both are compiled in only on request (-DSDRM_TRACE / -DSDRM_PERF_DEBUG).
+#ifdef SDRM_TRACE
+#define SDRM_TR(role, code) TR(role, code)
+#define SDRM_TR_SEQ() (++trace_seq)
+#define SDRM_TR_EPI(code) do { if (warp == 0 && lane == 0) TR(2, code); } while (0)
+#else
+#define SDRM_TR(role, code) do { } while (0)
+#define SDRM_TR_SEQ() do { } while (0)
+#define SDRM_TR_EPI(code) do { } while (0)
+#endif
+#ifdef SDRM_PERF_DEBUG
+#define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
+#define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
+#else
+#define SDRM_DEBUG_SKIP_ACT_STORES 0
+#define SDRM_DEBUG_SKIP_NOISE 0
+#endif
+
 namespace sdrm {
 
 namespace {
 
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
-
-// write 16 consecutive bf16 features [f0, f0+16) of tile row r into a k-block image buffer
-__device__ __forceinline__ void store_act16(uint8_t* buf, int r, int f0, const uint32_t (&pk)[8], uint64_t pol, bool skip = false) {
-  if (skip) return;
-  const int kb = f0 >> 6;
-  const int j0 = (f0 & 63) >> 3;   // even: the two 16-byte pieces share one aligned 32-byte sector of the swizzled row
-  const int sw = r & 7;
-  uint8_t* sector = buf + static_cast<size_t>(kb) * A_TILE_BYTES + r * 128 + (((j0 ^ sw) & ~1) << 4);
-  const bool flip = sw & 1;        // odd rows hold the pair in swapped order (128-byte swizzle XOR)
-  const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
-  const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
-  // one 256-bit store (STG.256): the stores scatter over 32 rows per warp, so halving their count halves the L1 cost
-  asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
-               ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol)
-               : "memory");
-}
 
 // fp32 state layout inside a tile: [16-col group][half 0..1][row 0..127][8 floats]; a thread moves its 16 columns with two
 // 256-bit streaming accesses (evict-first: the state must not push the activation images out of L2), a warp touches
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int n_iters = static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);
   auto tile_of = [&](int it) -> long long { return (static_cast<long long>(it) * n_clusters + my_cluster) * NCTA + cta_rank; };
   int* err = P.err_word;
+#ifdef SDRM_TRACE
   int trace_n = 0;
   const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp < W_WARP);
   unsigned long long trace_seq = 0;  // k-block sequence number of the role (for matching producer / consumer events)
@@ -158,13 +164,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     if (tracing && trace_n < TRACE_CAP && (trace_kb || !((role == 0 && (code == 4 || code == 5)) || (role == 1 && code >= 5))))
       P.trace[role * TRACE_CAP + trace_n++] = (code << 56) | ((trace_seq & 0xFFFFull) << 40) | (globaltimer_ns() & 0xFFFFFFFFFFull);
   };
+#endif
 
   auto scratch_of = [&](long long tile) -> uint8_t* {
     const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x);
     return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
   };
 
+  // setmaxnreg sits at the top of each role's own branch: ptxas budgets every program point with the smallest register
+  // count that can reach it, so a shared prologue would cap all roles at the control warps' budget
   if (warp == W_WARP || warp == A_WARP) {
+    setmaxnreg_dec<REGS_CTRL>();
     // ============================ TMA producers: warp 0 streams weights, warp 2 streams activations =========
     // The whole warp runs the loops CONVERGED and one elected lane issues the copies: single-lane (divergent) code makes
     // the compiler wrap every uniform-datapath instruction (UBLKCP / UTMALDG / UTCHMMA) in an elect loop and costs
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes, kind = ldref.kind;
         const uint8_t* w_img = ldref.w_img;
         int ready = 0;
-        if (!is_w) TR(0, 1);
+        if (!is_w) SDRM_TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
         const int half_rows = NC >> 1;
         const int part_rows = NC / CS;          // rows of a weight k-block this CTA fetches (CS >= 4: multicast to its peers)
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   act_par ^= (1u << ready);
                   ++ready;
                 }
-                if (kb == 0) TR(0, 2);
+                if (kb == 0) SDRM_TR(0, 2);
               }
               mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
               const uint32_t fb = bar_full(stage);
@@ -249,11 +259,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               a_row += A_TILE_BYTES >> 7;
               w_src += w_bytes;
               a_src += A_TILE_BYTES;
-              if (!is_w) { TR(0, 5); ++trace_seq; }
+              if (!is_w) { SDRM_TR(0, 5); SDRM_TR_SEQ(); }
               if (++stage == NSTG) { stage = 0; sphase ^= 1; }
             }
           }
-          if (!is_w) TR(0, 3);
+          if (!is_w) SDRM_TR(0, 3);
         }
         prev_nch = (kind == EPI_LINEAR_OUT) ? 0 : NCH;
         prev_nc = NC;
@@ -266,6 +276,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
     }
   } else if (warp == M_WARP) {
+    setmaxnreg_dec<REGS_CTRL>();
     if (PAIR && cta_rank != leader_rank) {
       // peer CTA of a pair: the leader issues every UMMA; the peer's TMA loads complete on the leader's barriers
     } else {
@@ -284,17 +295,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ldref.NC);
           for (int c = 0; c < NCH; ++c) {
             const uint32_t buf = cc & 1u;
-            TR(1, 1);
+            SDRM_TR(1, 1);
             mbar_wait(bar_acc_empty(buf), ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
             tc_fence_after();
-            TR(1, 2);
+            SDRM_TR(1, 2);
             const uint32_t d_tmem = tmem_base + buf * 256u;
             uint32_t acc = 0;
             for (int p = 0; p < passes; ++p) {
               for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
                 tc_fence_after();
-                TR(1, kb == 0 && p == 0 ? 3 : 5);
+                SDRM_TR(1, kb == 0 && p == 0 ? 3 : 5);
                 const uint64_t a_desc = umma_desc_sw128(stage_a(stage));
                 const uint64_t b_desc = umma_desc_sw128(stage_w(stage));
                 const int nk = (kb == KB - 1) ? kmma_last : 4;
@@ -316,8 +327,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 }
                 __syncwarp();
                 acc = 1;
-                TR(1, 6);
-                ++trace_seq;
+                SDRM_TR(1, 6);
+                SDRM_TR_SEQ();
                 if (++stage == NSTG) { stage = 0; sphase ^= 1; }
               }
             }
@@ -326,7 +337,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               else umma_commit(bar_acc_full(buf));
             }
             __syncwarp();
-            TR(1, 4);
+            SDRM_TR(1, 4);
             ++cc;
           }
         };
@@ -335,18 +346,48 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
       }
     }
+  } else if (warp > A_WARP) {
+    setmaxnreg_dec<REGS_CTRL>();   // idle fourth warp of the control warpgroup
   } else if (warp < EPI_WARPS) {
     // ======================================= epilogue warps =====================================
     // 16 warps: warp (q, sub) reads TMEM lane quarter q (rows 32q..32q+31) and owns the 16-column groups
     // g = sub (mod 4).  One thread always touches the same (row, columns) of the fp32 state, so the state
-    // needs no synchronisation at all.
+    // needs no synchronisation at all.  The SM's issue slots, not the tensor pipe, bound this kernel (ncu: ~150 k warp
+    // instructions per step and SM sub-partition against 173 k cycles of UMMA time), so the per-group code is specialised
+    // per layer kind, runs on packed f32x2 arithmetic and keeps every loop-invariant out of the loop.
+    setmaxnreg_inc<REGS_EPI>();
     const uint64_t pol_keep = l2_policy_evict_last();
     const int q = warp & 3;
     const int sub = warp >> 2;
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(r & 6) << 4;   // 128-byte swizzle of the row, 32-byte-sector part
+    const bool flip = r & 1;                                  // odd rows hold the two 16-byte pieces of a sector swapped
     uint32_t cc = 0;
     int it = 0;
+
+    // write 16 consecutive bf16 features [f0, f0+16) of this thread's row into a k-block image buffer: ONE 256-bit store
+    // (the stores scatter over 32 rows per warp, so their count is what costs)
+    auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
+      uint8_t* sector = buf_row + static_cast<size_t>(f0 >> 6) * A_TILE_BYTES + ((static_cast<uint32_t>(f0 & 48) << 1) ^ swz);
+      const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
+      const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
+      asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                   ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol_keep)
+                   : "memory");
+    };
+    // dropout (F.dropout p = .5: kept values are doubled) + bf16 pack of 16 state values
+    auto dropout_pack = [&](const float (&x)[16], uint32_t keep, uint32_t (&pk)[8]) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        // 2.0f = 0x40000000: the keep bit moved to bit 30 IS the scale factor (0 or 2)
+        const float s0 = __uint_as_float((keep << (30 - 2 * e)) & 0x40000000u);
+        const float s1 = __uint_as_float((keep << (29 - 2 * e)) & 0x40000000u);
+        const float2 m = __fmul2_rn(make_float2(x[2 * e], x[2 * e + 1]), make_float2(s0, s1));
+        pk[e] = pack_bf16x2(m.x, m.y);
+      }
+    };
 
     // zero the activation buffers once: K-padding columns must read as exact zeros
     if (!P.preloaded_input) {
@@ -361,6 +402,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       if (!PAIR && tile >= n_tiles) break;
       uint8_t* sc = scratch_of(tile);
       float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+      const uint16_t* mask_row = reinterpret_cast<const uint16_t*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
       const long long prow = tile * TILE_M + r;   // physical row of this launch
       const bool valid = prow < P.n_rows;
       const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
@@ -379,25 +421,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int w = 0; w < EPI_WARPS; ++w) T_tile = max(T_tile, warp_max[(it & 1) * EPI_WARPS + w]);
       if (P.n_step == 0) T_tile = 0;
 
-      auto keep_mask16 = [&](int step, int g16) -> uint32_t {
-        // bit b = keep flag of column 16*g16 + b at this step (F.dropout p = .5, train_SDRM.py:100)
-        if (!valid) return 0u;
-        if (P.inj_mask) {
-          uint32_t bits = 0;
-          const uint8_t* mp = P.inj_mask + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int f = g16 * 16 + e;
-            if (f < P.L && mp[f]) bits |= (1u << e);
-          }
-          return bits;
-        }
-        return philox_mask16(P.seed, STREAM_MASK, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16));
-      };
-
-      // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38); also the noise half of the first step
+      // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38).  Once per tile: not performance critical.
       if (P.n_step > 0) {
-        uint8_t* in0 = sc;   // the first chain layer reads activation buffer 0
+        const PhiloxKeys K = philox_make_keys(P.seed);
+        uint8_t* in0_row = sc + row_off;   // the first chain layer reads activation buffer 0
         for (int g = sub; g < P.Lg16; g += EPI_SUB) {
           float x[16];
 #pragma unroll
@@ -410,24 +437,34 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 z4[e] = (valid && f < P.L) ? P.inj_xT[static_cast<size_t>(row) * P.L + f] : 0.0f;
               }
             } else {
-              philox_normal4(P.seed, STREAM_NORMAL, grow, 0u, static_cast<uint32_t>(g * 4 + j), z4);
+              philox_normal4_keys(K, STREAM_NORMAL, grow, 0u, static_cast<uint32_t>(g * 4 + j), z4);
             }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int f = g * 16 + j * 4 + e;
-              x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;
+              x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;   // padding columns / rows stay exactly 0 for the whole chain
             }
           }
           xs_store16(xs, g, r, x);
-          const uint32_t keep = keep_mask16(T_tile, g);
-          uint32_t pk[8];
+          // keep mask of the first step (the noise warps produce the masks of all later steps)
+          uint32_t keep = 0;
+          if (valid) {
+            if (P.inj_mask) {
+              const uint8_t* mp = P.inj_mask + (static_cast<size_t>(T_tile) * P.n_rows + row) * P.L;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float a0 = ((keep >> (2 * e)) & 1u) ? 2.0f * x[2 * e] : 0.0f;
-            const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * x[2 * e + 1] : 0.0f;
-            pk[e] = pack_bf16x2(a0, a1);
+              for (int e = 0; e < 16; ++e) {
+                const int f = g * 16 + e;
+                if (f < P.L && mp[f]) keep |= (1u << e);
+              }
+            } else {
+              const u32x4 w4 = philox_mask128(K, STREAM_MASK, grow, static_cast<uint32_t>(T_tile), static_cast<uint32_t>(g >> 3));
+              const uint32_t wsel = ((g >> 1) & 3) == 0 ? w4.x : ((g >> 1) & 3) == 1 ? w4.y : ((g >> 1) & 3) == 2 ? w4.z : w4.w;
+              keep = (wsel >> (16 * (g & 1))) & 0xFFFFu;
+            }
           }
-          store_act16(in0, r, g * 16, pk, pol_keep);
+          uint32_t pk[8];
+          dropout_pack(x, keep, pk);
+          store_act(in0_row, g * 16, pk);
         }
       }
       if (warp == 0 && lane == 0) tile_T[it & 1] = T_tile;
@@ -435,51 +472,72 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tile_ready);
 
-      // ---- layers
-      auto run = [&](const LayerDesc& ld, int step, int layer_idx, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
-        uint8_t* out_hi = sc + static_cast<size_t>(out_hi_buf) * P.act_buf_bytes;
-        uint8_t* out_lo = sc + static_cast<size_t>(out_lo_buf) * P.act_buf_bytes;
+      // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
+      auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
+        constexpr int KIND = decltype(kind_c)::value;
+        uint8_t* out_hi_row = sc + static_cast<size_t>(out_hi_buf) * P.act_buf_bytes + row_off;
+        uint8_t* out_lo_row = sc + static_cast<size_t>(out_lo_buf) * P.act_buf_bytes + row_off;
         const float* bias_row = ld.bias + static_cast<size_t>(step) * ld.bias_step_stride;
-        const float slope = ld.slope ? __ldg(ld.slope) : 0.0f;
-        float c12 = 0.f;
-        const bool active = valid && (step <= t_row);
-        if (ld.kind == EPI_POSTERIOR) {
+        const int NC = ld.NC, NCH = ld.NCH, ngroups = NC >> 4, n_valid = ld.n_valid;
+        float slope = 0.0f, c12 = 0.0f;
+        bool slope01 = true;
+        if (KIND == EPI_PRELU) {
+          slope = __ldg(ld.slope);
+          slope01 = slope >= 0.0f && slope <= 1.0f;   // PReLU(h) = max(h, a h) for 0 <= a <= 1 (every trained SDRM slope; init 0.25)
+        }
+        if (KIND == EPI_POSTERIOR) {
           const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
-          c12 = active ? cf.x * cf.y : 0.0f;
-          // the noise warps have turned the state into x_i / sqrt(a_i) + sqrt(b_i) nd z_i for this step
+          c12 = (valid && step <= t_row) ? cf.x * cf.y : 0.0f;   // rows not started yet (multi-resolution) keep their state
+          // the noise warps have turned the state into x_i / sqrt(a_i) + sqrt(b_i) nd z_i and written the keep masks of step i-1
           mbar_wait_sleepy(bar_noise_ready, noise_par, err, WD_EPI_NOISE, 128);
           noise_par ^= 1;
         }
-        const int ngroups = ld.NC >> 4;
-        for (int c = 0; c < ld.NCH; ++c) {
+        const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
+        float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
+        const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT;
+        for (int c = 0; c < NCH; ++c) {
           const uint32_t buf = cc & 1u;
-          if (warp == 0 && lane == 0) TR(2, 1);
+          SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
-          if (warp == 0 && lane == 0) TR(2, 2);
+          SDRM_TR_EPI(2);
+          const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
+          const int fc = c * NC;
+#pragma unroll 1
           for (int g = sub; g < ngroups; g += EPI_SUB) {
+            const int f0 = fc + g * 16;
             uint32_t v[16];
-            tmem_ld16(tmem_base + lane_addr + buf * 256u + g * 16u, v);
-            const int f0 = c * ld.NC + g * 16;
+            tmem_ld16(t_chunk + g * 16u, v);
             float4 b4[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias_row + f0) + j);
+            // the posterior update needs this thread's state columns and keep bits: issue the loads before waiting on TMEM
+            float xn[16];
+            uint32_t keep = 0;
+            const int g16 = f0 >> 4;
+            if (KIND == EPI_POSTERIOR) {
+              if (g16 < P.Lg16) {
+                xs_load16(xs, g16, r, xn);
+                if (step > 1) keep = mask_row[g16];
+              }
+            }
             tmem_ld_wait();
             float h[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              h[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b4[j].x;
-              h[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b4[j].y;
-              h[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b4[j].z;
-              h[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b4[j].w;
+              const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b4[j].x, b4[j].y));
+              const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b4[j].z, b4[j].w));
+              h[4 * j] = lo.x; h[4 * j + 1] = lo.y; h[4 * j + 2] = hi.x; h[4 * j + 3] = hi.y;
             }
-            if (ld.kind == EPI_PRELU) {
+            if (KIND == EPI_PRELU) {
               uint32_t pk[8];
-              if (slope >= 0.0f && slope <= 1.0f) {
-                // PReLU(h) = max(h, a h) for 0 <= a <= 1 (every trained SDRM slope; init 0.25): FMUL + FMNMX per element
+              if (slope01) {
+                const float2 s2 = make_float2(slope, slope);
 #pragma unroll
-                for (int e = 0; e < 8; ++e)
-                  pk[e] = pack_bf16x2(fmaxf(h[2 * e], slope * h[2 * e]), fmaxf(h[2 * e + 1], slope * h[2 * e + 1]));
+                for (int e = 0; e < 8; ++e) {
+                  const float2 t = __fmul2_rn(make_float2(h[2 * e], h[2 * e + 1]), s2);
+                  pk[e] = pack_bf16x2(fmaxf(h[2 * e], t.x), fmaxf(h[2 * e + 1], t.y));
+                }
               } else {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -488,30 +546,23 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   pk[e] = pack_bf16x2(a0, a1);
                 }
               }
-              store_act16(out_hi, r, f0, pk, pol_keep, P.debug_flags & 1);
-            } else if (ld.kind == EPI_POSTERIOR) {
+              if (!SDRM_DEBUG_SKIP_ACT_STORES) store_act(out_hi_row, f0, pk);
+            } else if (KIND == EPI_POSTERIOR) {
               // x_{i-1} = (x_i - eps (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) nd z; the state already holds
-              // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise_group), so only the eps term is left.
-              const int g16 = f0 >> 4;
+              // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise warps), so only the eps term is left.  Padding columns need no
+              // masking: their weights and bias are 0, so eps = tanh(0) = 0 and the state stays exactly 0.
               if (g16 < P.Lg16) {
-                float xn[16];
-                xs_load16(xs, g16, r, xn);
+                const float2 nc = make_float2(-c12, -c12);
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const float nv = fmaf(-c12, fast_tanh(h[e]), xn[e]);
-                  xn[e] = (valid && f0 + e < P.L) ? nv : 0.0f;
+                for (int e = 0; e < 8; ++e) {
+                  const float2 nv = __ffma2_rn(nc, make_float2(fast_tanh(h[2 * e]), fast_tanh(h[2 * e + 1])), make_float2(xn[2 * e], xn[2 * e + 1]));
+                  xn[2 * e] = nv.x; xn[2 * e + 1] = nv.y;
                 }
                 xs_store16(xs, g16, r, xn);
                 if (step > 1) {
-                  const uint32_t keep = keep_mask16(step - 1, g16);
                   uint32_t pk[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float a0 = ((keep >> (2 * e)) & 1u) ? 2.0f * xn[2 * e] : 0.0f;
-                    const float a1 = ((keep >> (2 * e + 1)) & 1u) ? 2.0f * xn[2 * e + 1] : 0.0f;
-                    pk[e] = pack_bf16x2(a0, a1);
-                  }
-                  store_act16(out_hi, r, f0, pk, pol_keep);
+                  dropout_pack(xn, keep, pk);
+                  store_act(out_hi_row, f0, pk);
                 } else {
                   // last reverse step: hand x_0 to the decoder as bf16 hi/lo (bf16x3 GEMM)
                   uint32_t ph[8], pl[8];
@@ -521,8 +572,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     ph[e] = pack_bf16x2(h0, h1);
                     pl[e] = pack_bf16x2(xn[2 * e] - h0, xn[2 * e + 1] - h1);
                   }
-                  store_act16(out_hi, r, f0, ph, pol_keep);
-                  store_act16(out_lo, r, f0, pl, pol_keep);
+                  store_act(out_hi_row, f0, ph);
+                  store_act(out_lo_row, f0, pl);
                   if (P.x0_out && valid) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e)
@@ -530,7 +581,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   }
                 }
               }
-            } else if (ld.kind == EPI_TANH_SPLIT) {
+            } else if (KIND == EPI_TANH_SPLIT) {
               uint32_t ph[8], pl[8];
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -539,20 +590,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 ph[e] = pack_bf16x2(h0, h1);
                 pl[e] = pack_bf16x2(t0 - h0, t1 - h1);
               }
-              store_act16(out_hi, r, f0, ph, pol_keep);
-              store_act16(out_lo, r, f0, pl, pol_keep);
+              store_act(out_hi_row, f0, ph);
+              store_act(out_lo_row, f0, pl);
             } else {  // EPI_LINEAR_OUT
               if (valid) {
-                float* orow = P.logits + static_cast<size_t>(row) * P.ld_logits;
-                if (((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0) &&
-                    (f0 + 16 <= ld.n_valid)) {
+                if (vec_out && (f0 + 16 <= n_valid)) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
                     __stcs(reinterpret_cast<float4*>(orow + f0) + j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
                 } else {
 #pragma unroll
                   for (int e = 0; e < 16; ++e)
-                    if (f0 + e < ld.n_valid) orow[f0 + e] = h[e];
+                    if (f0 + e < n_valid) orow[f0 + e] = h[e];
                 }
               }
             }
@@ -563,43 +612,56 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), leader_rank));   // the leader CTA issues the UMMAs
             else mbar_arrive(bar_acc_empty(buf));
           }
-          if (warp == 0 && lane == 0) TR(2, 3);
+          SDRM_TR_EPI(3);
           ++cc;
           // publish this chunk's activations to the TMA (async) proxy and tell the A producer
-          const bool publishes = !last_of_tile && ld.kind != EPI_LINEAR_OUT;
-          auto publish = [&]() {
+          if (publishes) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_act_chunk(c));
-            if (warp == 0 && lane == 0) TR(2, 5);
-          };
-          if (publishes) publish();
+            SDRM_TR_EPI(5);
+          }
         }
-        if (ld.kind == EPI_POSTERIOR && step > 1) {
+        if (KIND == EPI_POSTERIOR && step > 1) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_state_ready);   // x_{i-1} is complete: the noise warps may prepare step i-1
+        }
+      };
+      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
+        switch (ld.kind) {
+          case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
+          case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
+          case EPI_TANH_SPLIT: run(std::integral_constant<int, EPI_TANH_SPLIT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
+          default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
         }
       };
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
         for (int l = 0; l < P.n_step; ++l) {
-          run(P.step[l], i, l, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2);   // x0 lo -> buffer 2
+          run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2);   // x0 lo -> buffer 2
           cur ^= 1;
         }
-      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], 0, l, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo);
+      for (int l = 0; l < P.n_dec; ++l) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo);
     }
   } else {
     // ======================================= noise warps ========================================
-    // Thread r owns tile row r.  For every step i it turns the fp32 state x_i into x_i / sqrt(a_i) + sqrt(b_i) nd z_i
-    // (the part of the DDPM posterior that does not depend on the network) while the tensor core and the epilogue warps
-    // run the step's dense layers; z comes from the Philox stream keyed by (global row, step, column).
+    // Thread r owns tile row r.  For every step i it (1) writes the dropout keep bits of step i-1 (one Philox call per 128
+    // columns; the OUT epilogue of step i applies them to x_{i-1}) and (2) turns the fp32 state x_i into
+    // x_i / sqrt(a_i) + sqrt(b_i) nd z_i (the part of the DDPM posterior that does not depend on the network) while the
+    // tensor core and the epilogue warps run the step's dense layers; z comes from the Philox stream keyed by
+    // (global row, step, column).
+    setmaxnreg_dec<REGS_NOISE>();
     const int r = (warp - NOISE_WARP0) * 32 + lane;
+    const PhiloxKeys K = philox_make_keys(P.seed);
     uint32_t st_par = 0;
+    const int L = P.L, Lg16 = P.Lg16;
+    const int full_groups = L >> 4;          // groups without padding columns
     for (int it = 0; it < n_iters; ++it) {
       const long long tile = tile_of(it);
       if (!PAIR && tile >= n_tiles) break;
       uint8_t* sc = scratch_of(tile);
       float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+      uint4* mask_row = reinterpret_cast<uint4*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
       const long long prow = tile * TILE_M + r;
       const bool valid = prow < P.n_rows;
       const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;
@@ -608,51 +670,81 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
       mbar_wait_sleepy(bar_tile_ready, it & 1, err, WD_NOISE_TILE, 128);   // x_T is in place
       const int T_tile = (P.n_step == 0) ? 0 : tile_T[it & 1];
-      // Noise half of the posterior update, done AHEAD of the eps GEMM of the same step (z does not depend on the
-      // network): state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
-      auto noise_group = [&](int step, int g16) {
-        if (P.debug_flags & 4) return;
-        const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
-        const bool active = valid && (step <= t_row);
-        if (!active) return;  // inactive (multi-resolution) or padding rows keep their state
-        const float c2 = cf.y, sg = cf.z;
-        // issue the four state loads first (they stream from L2 / HBM), then generate the four Philox quads (independent
-        // chains the compiler interleaves), then update
-        float xo[16];
-        xs_load16(xs, g16, r, xo);
-        float z[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) z[j][e] = 0.0f;
-          if (sg != 0.0f) {
-            if (P.inj_z) {
-              const float* zp = P.inj_z + (static_cast<size_t>(step) * P.n_rows + row) * P.L;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int f = g16 * 16 + 4 * j + e;
-                z[j][e] = f < P.L ? zp[f] : 0.0f;
-              }
-            } else {
-              philox_normal4(P.seed, STREAM_NORMAL, grow, static_cast<uint32_t>(step), static_cast<uint32_t>(g16 * 4 + j), z[j]);
-            }
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int f = g16 * 16 + 4 * j + e;
-            xo[4 * j + e] = (f < P.L) ? fmaf(sg, z[j][e], xo[4 * j + e] * c2) : 0.0f;
-          }
-        xs_store16(xs, g16, r, xo);
-      };
       for (int i = T_tile; i >= 1; --i) {
         if (i != T_tile) {
           mbar_wait_sleepy(bar_state_ready, st_par, err, WD_NOISE_STATE, 128);
           st_par ^= 1;
         }
-        for (int g = 0; g < P.Lg16; ++g) noise_group(i, g);
+        // ---- (1) keep masks of step i-1 (F.dropout p = .5 of the NEXT forward, train_SDRM.py:100)
+        if (i > 1) {
+          const int nblk = (Lg16 + 7) >> 3;
+          for (int b = 0; b < nblk; ++b) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (valid) {
+              if (P.inj_mask) {
+                const uint8_t* mp = P.inj_mask + (static_cast<size_t>(i - 1) * P.n_rows + row) * L;
+                uint32_t ww[4] = {0, 0, 0, 0};
+                for (int e = 0; e < 128; ++e) {
+                  const int f = b * 128 + e;
+                  if (f < L && mp[f]) ww[e >> 5] |= 1u << (e & 31);
+                }
+                w = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+              } else {
+                const u32x4 m4 = philox_mask128(K, STREAM_MASK, grow, static_cast<uint32_t>(i - 1), static_cast<uint32_t>(b));
+                w = make_uint4(m4.x, m4.y, m4.z, m4.w);
+              }
+            }
+            mask_row[b] = w;
+          }
+        }
+        // ---- (2) noise half of the posterior update, AHEAD of the eps GEMM of the same step:
+        //      state := state / sqrt(a_i) + sqrt(b_i) nd z_i.  The OUT epilogue then only subtracts eps * c1 / sqrt(a_i).
+        const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + i);
+        const bool active = valid && (i <= t_row);   // inactive (multi-resolution) or padding rows keep their state
+        if (active && !SDRM_DEBUG_SKIP_NOISE) {
+          const float2 c2 = make_float2(cf.y, cf.y), sg = make_float2(cf.z, cf.z);
+          const bool has_z = cf.z != 0.0f;
+          auto group = [&](int g16, bool padded) {
+            float xo[16];
+            xs_load16(xs, g16, r, xo);
+            float z[16];
+            if (has_z) {
+              if (P.inj_z) {
+                const float* zp = P.inj_z + (static_cast<size_t>(i) * P.n_rows + row) * L;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const int f = g16 * 16 + e;
+                  z[e] = f < L ? zp[f] : 0.0f;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float z4[4];
+                  philox_normal4_keys(K, STREAM_NORMAL, grow, static_cast<uint32_t>(i), static_cast<uint32_t>(g16 * 4 + j), z4);
+                  z[4 * j] = z4[0]; z[4 * j + 1] = z4[1]; z[4 * j + 2] = z4[2]; z[4 * j + 3] = z4[3];
+                }
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) z[e] = 0.0f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float2 t = __fmul2_rn(make_float2(xo[2 * e], xo[2 * e + 1]), c2);
+              const float2 n = __ffma2_rn(sg, make_float2(z[2 * e], z[2 * e + 1]), t);
+              xo[2 * e] = n.x; xo[2 * e + 1] = n.y;
+            }
+            if (padded) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (g16 * 16 + e >= L) xo[e] = 0.0f;   // padding columns stay exactly 0
+            }
+            xs_store16(xs, g16, r, xo);
+          };
+#pragma unroll 1
+          for (int g = 0; g < full_groups; ++g) group(g, false);
+          if (full_groups < Lg16) group(full_groups, true);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_noise_ready);
       }

@@ -24,6 +24,13 @@ def test_normals_and_masks_statistics():
     m = ph.keep_masks(12345, ph.STREAM_MASK, np.arange(2000), 3, 250)
     assert m.shape == (2000, 250) and set(np.unique(m)) == {0, 1}
     assert abs(m.mean() - 0.5) < 0.005
+    m = ph.keep_masks128(12345, ph.STREAM_MASK, np.arange(2000), 3, 250)
+    assert m.shape == (2000, 250) and set(np.unique(m)) == {0, 1}
+    assert abs(m.mean() - 0.5) < 0.005
+    # column 128*b + 32*w + j is bit j of word w of the Philox block b
+    w = ph.philox4x32_10(np.uint32(1), np.uint32(3), np.uint32(7), np.uint32(ph.STREAM_MASK), 12345, 0)
+    one = ph.keep_masks128(12345, ph.STREAM_MASK, np.array([7]), 3, 256)[0]
+    assert all(int(one[128 + 32 * k + j]) == (int(w[k]) >> j) & 1 for k in range(4) for j in range(32))
 
 
 def test_streams_are_keyed_by_global_row():

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsdrm_b200.so")
+LIB_PATH = os.environ.get("SDRM_B200_LIB") or os.path.join(_HERE, "csrc", "libsdrm_b200.so")   # override: tuning builds only
 
 _lib = None
 

@@ -30,7 +30,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """extra_flags / out: tuning variants (e.g. -DSDRM_NSTG_PAIR=6 -> another .so selected with SDRM_B200_LIB)."""
+    global LIB
+    if out:
+        LIB = os.path.join(HERE, out)
+        force = True
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
@@ -40,8 +45,8 @@ def build(force=False, verbose=False):
         src = os.path.join(HERE, s)
         if not os.path.exists(src):
             continue
-        obj = os.path.join(HERE, s.replace(".cu", ".o"))
-        cmd = [nvcc] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-dc" if False else "-c", src, "-o", obj]
+        obj = os.path.join(HERE, s.replace(".cu", ".o" if not out else "." + out + ".o"))
+        cmd = [nvcc] + FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-dc" if False else "-c", src, "-o", obj]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for s, p in procs:
@@ -59,4 +64,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=extra, out=outs[0] if outs else None))

@@ -32,6 +32,9 @@
 #define SDRM_TR_SEQ() do { } while (0)
 #define SDRM_TR_EPI(code) do { } while (0)
 #endif
+#ifndef SDRM_NSTG_PAIR
+#define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 measured no faster and leaves no room for the bias slices
+#endif
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
 #define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
@@ -87,11 +90,12 @@ template <int CS>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
   constexpr bool PAIR = CS >= 2;
   constexpr int NPAIRS = PAIR ? CS / 2 : 1;
-  constexpr int NSTG = PAIR ? 7 : 4;
+  constexpr int NSTG = PAIR ? SDRM_NSTG_PAIR : 4;
   constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = CS;
-  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
+  constexpr uint32_t BIAS_SLICE_BYTES = 4 * 16 * 4;   // per epilogue warp: the bias of its (at most 4) column groups of one chunk
+  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 256 + EPI_WARPS * BIAS_SLICE_BYTES + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
+  uint8_t* bias_slices = smem + ((NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 15) & ~15);   // EPI_WARPS x BIAS_SLICE_BYTES, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t swz = static_cast<uint32_t>(r & 6) << 4;   // 128-byte swizzle of the row, 32-byte-sector part
     const bool flip = r & 1;                                  // odd rows hold the two 16-byte pieces of a sector swapped
+    float* bias_s = reinterpret_cast<float*>(bias_slices + warp * BIAS_SLICE_BYTES);   // this warp's private bias slice
     uint32_t cc = 0;
     int it = 0;
 
@@ -495,40 +501,57 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
         const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT;
+        // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
+        // warp stages the 64 floats of its own groups of a chunk in a private shared-memory slice (lane l holds elements
+        // 2l, 2l+1: group slot l / 8, columns 2 (l % 8) ..) one chunk ahead, and the group loop reads them with LDS.128.
+        const int slice_g = sub + EPI_SUB * (lane >> 3);            // group whose bias this lane fetches
+        const int slice_o = slice_g * 16 + 2 * (lane & 7);
+        auto fetch_slice = [&](int c) -> float2 {
+          return (slice_g < ngroups) ? *reinterpret_cast<const float2*>(bias_row + c * NC + slice_o) : make_float2(0.f, 0.f);
+        };
+        float2 bnext = fetch_slice(0);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t buf = cc & 1u;
+          const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
+          const int fc = c * NC;
+          __syncwarp();                                             // every lane is done with the previous chunk's slice
+          *reinterpret_cast<float2*>(bias_s + 2 * lane) = bnext;
+          __syncwarp();
+          if (c + 1 < NCH) bnext = fetch_slice(c + 1);
+          // Software pipeline over this warp's groups: the TMEM load (and, for the posterior update, the state columns and
+          // keep bits) of group g+4 is requested as soon as group g has consumed its own, so its latency hides behind the
+          // arithmetic and the store of group g.
+          uint32_t v[16];
+          float xn[16];
+          uint32_t keep = 0;
+          auto request_state = [&](int g) {
+            const int g16 = (fc >> 4) + g;
+            if (g16 < P.Lg16) {
+              xs_load16(xs, g16, r, xn);
+              if (step > 1) keep = mask_row[g16];
+            }
+          };
+          if (KIND == EPI_POSTERIOR && sub < ngroups) request_state(sub);   // does not depend on the accumulator: ask before waiting
           SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
-          const int fc = c * NC;
+          if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
+          const float4* bs = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll 1
-          for (int g = sub; g < ngroups; g += EPI_SUB) {
+          for (int g = sub; g < ngroups; g += EPI_SUB, bs += 4) {
             const int f0 = fc + g * 16;
-            uint32_t v[16];
-            tmem_ld16(t_chunk + g * 16u, v);
-            float4 b4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias_row + f0) + j);
-            // the posterior update needs this thread's state columns and keep bits: issue the loads before waiting on TMEM
-            float xn[16];
-            uint32_t keep = 0;
             const int g16 = f0 >> 4;
-            if (KIND == EPI_POSTERIOR) {
-              if (g16 < P.Lg16) {
-                xs_load16(xs, g16, r, xn);
-                if (step > 1) keep = mask_row[g16];
-              }
-            }
             tmem_ld_wait();
             float h[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b4[j].x, b4[j].y));
-              const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b4[j].z, b4[j].w));
+              const float4 b = bs[j];
+              const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
+              const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
               h[4 * j] = lo.x; h[4 * j + 1] = lo.y; h[4 * j + 2] = hi.x; h[4 * j + 3] = hi.y;
             }
+            if (g + EPI_SUB < ngroups) tmem_ld16(t_chunk + (g + EPI_SUB) * 16u, v);
             if (KIND == EPI_PRELU) {
               uint32_t pk[8];
               if (slope01) {
@@ -580,6 +603,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                       if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = xn[e];
                   }
                 }
+                if (g + EPI_SUB < ngroups) request_state(g + EPI_SUB);   // xn is dead: fetch the next group's state columns
               }
             } else if (KIND == EPI_TANH_SPLIT) {
               uint32_t ph[8], pl[8];
@@ -704,42 +728,51 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         if (active && !SDRM_DEBUG_SKIP_NOISE) {
           const float2 c2 = make_float2(cf.y, cf.y), sg = make_float2(cf.z, cf.z);
           const bool has_z = cf.z != 0.0f;
-          auto group = [&](int g16, bool padded) {
-            float xo[16];
-            xs_load16(xs, g16, r, xo);
-            float z[16];
+          // 8 columns (one 256-bit state access, two Philox calls) at a time keeps this role inside its small register budget
+          auto half_group = [&](int g16, int hf, bool padded) {
+            float xo[8];
+            float* px = xstate_ptr8(xs, g16, hf, r);
+            asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=f"(xo[0]), "=f"(xo[1]), "=f"(xo[2]), "=f"(xo[3]), "=f"(xo[4]), "=f"(xo[5]), "=f"(xo[6]), "=f"(xo[7])
+                         : "l"(px)
+                         : "memory");
+            float z[8];
+            const int f0 = g16 * 16 + hf * 8;
             if (has_z) {
               if (P.inj_z) {
                 const float* zp = P.inj_z + (static_cast<size_t>(i) * P.n_rows + row) * L;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) {
-                  const int f = g16 * 16 + e;
-                  z[e] = f < L ? zp[f] : 0.0f;
-                }
+                for (int e = 0; e < 8; ++e) z[e] = (f0 + e) < L ? zp[f0 + e] : 0.0f;
               } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                   float z4[4];
-                  philox_normal4_keys(K, STREAM_NORMAL, grow, static_cast<uint32_t>(i), static_cast<uint32_t>(g16 * 4 + j), z4);
+                  philox_normal4_keys(K, STREAM_NORMAL, grow, static_cast<uint32_t>(i), static_cast<uint32_t>(g16 * 4 + hf * 2 + j), z4);
                   z[4 * j] = z4[0]; z[4 * j + 1] = z4[1]; z[4 * j + 2] = z4[2]; z[4 * j + 3] = z4[3];
                 }
               }
             } else {
 #pragma unroll
-              for (int e = 0; e < 16; ++e) z[e] = 0.0f;
+              for (int e = 0; e < 8; ++e) z[e] = 0.0f;
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
+            for (int e = 0; e < 4; ++e) {
               const float2 t = __fmul2_rn(make_float2(xo[2 * e], xo[2 * e + 1]), c2);
               const float2 n = __ffma2_rn(sg, make_float2(z[2 * e], z[2 * e + 1]), t);
               xo[2 * e] = n.x; xo[2 * e + 1] = n.y;
             }
             if (padded) {
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (g16 * 16 + e >= L) xo[e] = 0.0f;   // padding columns stay exactly 0
+              for (int e = 0; e < 8; ++e)
+                if (f0 + e >= L) xo[e] = 0.0f;   // padding columns stay exactly 0
             }
-            xs_store16(xs, g16, r, xo);
+            asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"l"(px), "f"(xo[0]), "f"(xo[1]), "f"(xo[2]), "f"(xo[3]), "f"(xo[4]), "f"(xo[5]), "f"(xo[6]), "f"(xo[7])
+                         : "memory");
+          };
+          auto group = [&](int g16, bool padded) {
+            half_group(g16, 0, padded);
+            half_group(g16, 1, padded);
           };
 #pragma unroll 1
           for (int g = 0; g < full_groups; ++g) group(g, false);

@@ -206,23 +206,34 @@ def run_ours(args, w, rank, world, local_rank):
     total_ms = float(t.item())
     value = world * n * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end: rows land in pinned host memory (what main.py's .cpu().numpy() consumes)
+    # ---- end to end through the public call with HOST buffers: every step uploads the trained weights from pinned host
+    #      memory (the checkpoint a caller holds), re-packs them, samples, and delivers the rows into pinned host memory
+    #      (what main.py's .cpu().numpy() consumes)
     e2e = None
     if not args.no_e2e:
         host = torch.empty((n, w["I"]), dtype=torch.float32, pin_memory=True)
-        sample_ddpm_host(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=5, row_offset=row_offset, host_out=host)
+        params = [p for p in list(diff.parameters()) + list(vae.decoder.parameters())]
+        host_w = [p.detach().cpu().pin_memory() for p in params]
+        h2d_bytes = sum(t.numel() * t.element_size() for t in host_w)
+
+        def e2e_step(seed):
+            for p, hw in zip(params, host_w):
+                p.data.copy_(hw, non_blocking=True)   # H2D; bumps the tensor version, so the engine re-packs the weights
+            sample_ddpm_host(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=seed, row_offset=row_offset, host_out=host)
+
+        e2e_step(5)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
-            sample_ddpm_host(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=3000 + i, row_offset=row_offset,
-                             host_out=host)
+            e2e_step(3000 + i)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * n * args.e2e_steps / float(dt.item()), "unit": "users/s", "h2d_bytes_per_step": 0,
+        e2e = {"value": world * n * args.e2e_steps / float(dt.item()), "unit": "users/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": n * w["I"] * 4, "steps": args.e2e_steps,
-               "note": "sample_ddpm_host: chunked chain+decode with the D2H of chunk c overlapping chunk c+1"}
+               "note": "per step: weights H2D from pinned memory + re-pack, sample_ddpm_host (chunked chain+decode, the D2H of "
+                       "chunk c overlaps chunk c+1), rows land in pinned host memory; wall clock incl. all copies"}
         del host
 
     if rank == 0:
@@ -230,8 +241,16 @@ def run_ours(args, w, rank, world, local_rank):
         F = flops_per_user(w)
         kernel_ms = statistics.mean(step_ms)  # one persistent kernel per step
         achieved = F * n / (kernel_ms * 1e-3) / 1e12
+        traffic, traffic_src = None, None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath) and args.workload == "cfg5":
+            with open(tpath) as fh:
+                tj = json.load(fh)
+            traffic = tj["dram_bytes_per_user"] * n   # one launch processes n users
+            traffic_src = tj["source"]
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                    "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"] + " sustained bf16",
+                    "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peaks["source"] + " sustained bf16",
                     "kernel": "sdrm_layer_engine_kernel", "kernel_ms": kernel_ms, "flops_per_user": F,
                     "hbm_min_bytes_per_user": 4 * w["I"],
                     "hbm_frac_of_logits_write": (4 * w["I"] * n / (kernel_ms * 1e-3) / 1e9) / peaks["hbm"]}

@@ -41,7 +41,15 @@ def build_parser():
 
 
 def equal_sparsity(scores, sparsity):
-    """Binarise so the synthetic matrix keeps the training sparsity (main.py:177-185)."""
+    """Binarise so the synthetic matrix keeps the training sparsity (main.py:177-185).
+
+    CUDA score matrices never leave the GPU as floats: kernel K4 finds np.quantile's threshold with an exact radix select
+    and ships 1 bit per entry (sdrm_b200/sparsify.py); the result is identical to the reference's host-side lines.
+    Host arrays (VAE.sample returns a NumPy array in the reference too, main.py:183) take the reference's own two lines."""
+    import torch
+    if isinstance(scores, torch.Tensor):
+        from sdrm_b200.sparsify import equal_sparsity_device
+        return equal_sparsity_device(scores.detach(), sparsity).numpy(int)
     return (scores >= np.quantile(scores.flatten(), sparsity)).astype(int)
 
 
@@ -85,10 +93,10 @@ def main(argv=None):
 
         print("Sampling Multi-resolution Data")
         M_SDRM = sample_ddpm(N_USERS, SDRM, VAE, args.MLP_latent_neurons, args.SDRM_noise_variance_diminisher,
-                             timesteps="random", n_timesteps=args.SDRM_timesteps, verbose=True).detach().cpu().numpy()
+                             timesteps="random", n_timesteps=args.SDRM_timesteps, verbose=True)
         print("Sampling Full-resolution Data")
         F_SDRM = sample_ddpm(N_USERS, SDRM, VAE, args.MLP_latent_neurons, args.SDRM_noise_variance_diminisher,
-                             n_timesteps=args.SDRM_timesteps, verbose=True).detach().cpu().numpy()
+                             n_timesteps=args.SDRM_timesteps, verbose=True)
         synth = {
             "M-SDRM": pd.DataFrame(equal_sparsity(M_SDRM, SPARSITY)),
             "F-SDRM": pd.DataFrame(equal_sparsity(F_SDRM, SPARSITY)),

@@ -1,0 +1,210 @@
+// K4 — equal-sparsity thresholding of the synthetic score matrix on the device
+// (reference: main.py:177-185, 259-262 and hyperparameter_search.py:162-166:
+//   threshold = np.quantile(S.flatten(), SPARSITY);  S_bin = (S >= threshold).astype(int)
+//   lower tail for the NeuMF negatives: S <= np.quantile(S.flatten(), 1 - SPARSITY)).
+//
+// The reference sorts/partitions the whole [n, I] float32 matrix on the host (80 GB at the scale-up shape).
+// Here the two order statistics np.quantile interpolates between are found EXACTLY by a radix select over
+// order-preserving 32-bit keys: three histogram passes (11 + 11 + 10 bits) that each read the matrix once
+// (HBM-bound: 4 bytes per score), with the 2048-bin histograms summed across GPUs between passes when the rows
+// are sharded.  A last pass compares against the threshold and emits 1 bit per score (32x less D2H / gather
+// traffic than the fp32 matrix) plus the number of ones.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/sdrm_b200.h"
+#include "host_util.h"
+
+namespace sdrm {
+
+constexpr int HIST_BINS = 2048;
+constexpr int HIST_THREADS = 256;   // 8 warp-private histograms = 64 KB per block, 3 blocks per SM
+constexpr int HIST_WARPS = HIST_THREADS / 32;
+
+// float -> uint32 whose unsigned order is the float order (-inf < ... < -0 < +0 < ... < +inf < NaN)
+__device__ __forceinline__ uint32_t score_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct MatView {
+  const float* x;
+  long long rows, ld;
+  int n_cols;
+};
+
+// Calls f(value) for every score of the view; float4 loads when the layout allows, grid-stride over the matrix.
+template <typename F>
+__device__ __forceinline__ void for_each_score(const MatView& m, F&& f) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = ((m.n_cols & 3) == 0) && ((m.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.x) & 15) == 0);
+  if (vec) {
+    const long long c4 = m.n_cols >> 2;
+    const long long total = m.rows * c4;
+    if (m.ld == m.n_cols) {   // contiguous: plain 1-D sweep, four independent 16-byte loads in flight per thread
+      const float4* p = reinterpret_cast<const float4*>(m.x);
+      long long i = tid;
+      for (; i + 3 * nth < total; i += 4 * nth) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(p + i + u * nth);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { f(v[u].x); f(v[u].y); f(v[u].z); f(v[u].w); }
+      }
+      for (; i < total; i += nth) {
+        const float4 v = __ldcs(p + i);
+        f(v.x); f(v.y); f(v.z); f(v.w);
+      }
+    } else {
+      for (long long i = tid; i < total; i += nth) {
+        const long long r = i / c4, c = i - r * c4;
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(m.x + r * m.ld) + c);
+        f(v.x); f(v.y); f(v.z); f(v.w);
+      }
+    }
+  } else {
+    const long long total = m.rows * m.n_cols;
+    for (long long i = tid; i < total; i += nth) {
+      const long long r = i / m.n_cols, c = i - r * m.n_cols;
+      f(__ldcs(m.x + r * m.ld + c));
+    }
+  }
+}
+
+// One radix-select pass: histogram of the `bits`-wide digit at `shift` over the keys whose top `prefix_bits` bits equal
+// `prefix`; each warp keeps a private shared-memory histogram (no inter-warp conflicts), merged into global memory once.
+__global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint32_t prefix, int prefix_bits, int shift, int bits,
+                                                               unsigned long long* __restrict__ hist) {
+  extern __shared__ uint32_t sh[];   // [HIST_WARPS][HIST_BINS]
+  for (int i = threadIdx.x; i < HIST_WARPS * HIST_BINS; i += HIST_THREADS) sh[i] = 0;
+  __syncthreads();
+  uint32_t* mine = sh + (threadIdx.x >> 5) * HIST_BINS;
+  const uint32_t mask = (1u << bits) - 1u;
+  const int pshift = 32 - prefix_bits;
+  auto add = [&](float v) {
+    const uint32_t k = score_key(v);
+    // Plain shared-memory atomics on the warp-private histogram.  Even for the first digit, whose distribution is extremely
+    // skewed (a handful of exponent values), the hardware's in-warp conflict serialisation is 4.7x faster than merging
+    // equal bins with match.any first (measured on B200: 2.08 ms vs 9.69 ms for 10 GB).
+    if (prefix_bits == 0 || (k >> pshift) == prefix) atomicAdd(mine + ((k >> shift) & mask), 1u);
+  };
+  for_each_score(m, add);
+  __syncthreads();
+  for (int b = threadIdx.x; b < HIST_BINS; b += HIST_THREADS) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int w = 0; w < HIST_WARPS; ++w) s += sh[w * HIST_BINS + b];
+    if (s) atomicAdd(hist + b, s);
+  }
+}
+
+// bits[row][w] bit j = (score[row][32 w + j] >= thr)  (mode 0)  or  <= thr (mode 1).  A warp walks whole rows: every lane
+// loads 4 consecutive scores (a 512-byte coalesced warp load, two in flight), forms its 4-bit nibble and three xor-shuffles
+// assemble the four 32-bit words of the 128 columns.
+__global__ void __launch_bounds__(256) threshold_pack_kernel(MatView m, float thr, int mode, uint32_t* __restrict__ bits,
+                                                             long long words_per_row, unsigned long long* __restrict__ count) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const bool vec = ((m.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.x) & 15) == 0);
+  const int n_cols = m.n_cols;
+  unsigned long long ones = 0;
+  auto hit = [&](float v) { return mode == 0 ? (v >= thr) : (v <= thr); };
+  for (long long r = warp; r < m.rows; r += n_warps) {
+    const float* x = m.x + r * m.ld;
+    uint32_t* out = bits + r * words_per_row;
+    for (int c0 = 0; c0 < n_cols; c0 += 256) {
+      uint32_t nib[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * 128 + lane * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool ok[4] = {c < n_cols, c + 1 < n_cols, c + 2 < n_cols, c + 3 < n_cols};
+        if (vec && ok[3]) {
+          v = __ldcs(reinterpret_cast<const float4*>(x + c));
+        } else {
+          if (ok[0]) v.x = __ldcs(x + c);
+          if (ok[1]) v.y = __ldcs(x + c + 1);
+          if (ok[2]) v.z = __ldcs(x + c + 2);
+          if (ok[3]) v.w = __ldcs(x + c + 3);
+        }
+        nib[u] = (ok[0] && hit(v.x) ? 1u : 0u) | (ok[1] && hit(v.y) ? 2u : 0u) | (ok[2] && hit(v.z) ? 4u : 0u) | (ok[3] && hit(v.w) ? 8u : 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        // lane l holds columns 4l..4l+3 of this 128-column block: word l/8, bits 4 (l%8) ..
+        uint32_t w = nib[u] << (4 * (lane & 7));
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        const int word = (c0 + u * 128) / 32 + (lane >> 3);
+        if ((lane & 7) == 0 && word * 32 < n_cols) {
+          out[word] = w;
+          ones += __popc(w);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+  if (count && lane == 0 && ones) atomicAdd(count, ones);
+}
+
+static int grid_for(long long work_items, int threads, int per_thread, int blocks_per_sm) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long blocks = (work_items + static_cast<long long>(threads) * per_thread - 1) / (static_cast<long long>(threads) * per_thread);
+  const long long cap = static_cast<long long>(sms) * blocks_per_sm;   // one resident wave: a multiple of the SM count
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace sdrm
+
+using namespace sdrm;
+
+extern "C" {
+
+int sdrm_key_histogram(const float* d_scores, int64_t rows, int n_cols, int64_t ld, uint32_t prefix, int prefix_bits,
+                       int shift, int bits, unsigned long long* d_hist, void* stream) {
+  if (!d_scores || !d_hist) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_key_histogram: null pointer");
+  if (rows < 0 || n_cols <= 0 || ld < n_cols) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_key_histogram: bad shape");
+  if (bits < 1 || bits > 11 || shift < 0 || shift + bits > 32 || prefix_bits < 0 || prefix_bits > 31 || prefix_bits + bits + shift != 32)
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_key_histogram: digit layout (prefix_bits + bits + shift must be 32, bits <= 11)");
+  if (rows == 0) return SDRM_OK;
+  static bool attr_done = false;
+  const int smem = HIST_WARPS * HIST_BINS * static_cast<int>(sizeof(uint32_t));   // 64 KB
+  if (!attr_done) {
+    SDRM_CUDA(cudaFuncSetAttribute(key_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  MatView m{d_scores, rows, ld, n_cols};
+  const int grid = grid_for(rows * static_cast<long long>(n_cols), HIST_THREADS, 64, 3);
+  key_hist_kernel<<<grid, HIST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(m, prefix, prefix_bits, shift, bits, d_hist);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_threshold_pack(const float* d_scores, int64_t rows, int n_cols, int64_t ld, double threshold, int mode,
+                        uint32_t* d_bits, int64_t words_per_row, unsigned long long* d_count, void* stream) {
+  if (!d_scores || !d_bits) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_threshold_pack: null pointer");
+  if (rows < 0 || n_cols <= 0 || ld < n_cols || words_per_row < (n_cols + 31) / 32 || (mode != 0 && mode != 1))
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_threshold_pack: bad shape / mode");
+  if (rows == 0) return SDRM_OK;
+  MatView m{d_scores, rows, ld, n_cols};
+  // The scores are float32: x >= t (double) is the same predicate as x >= the smallest float32 not below t (and x <= t the
+  // same as x <= the largest float32 not above t), so the device compares in fp32 (B200 runs FP64 at a fraction of the rate).
+  float tf = static_cast<float>(threshold);
+  if (mode == 0 && static_cast<double>(tf) < threshold) tf = nextafterf(tf, INFINITY);
+  if (mode == 1 && static_cast<double>(tf) > threshold) tf = nextafterf(tf, -INFINITY);
+  const int grid = grid_for(rows * 32, 256, 1, 8);   // one warp per row until the wave is full
+  threshold_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, mode, d_bits, words_per_row, d_count);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+}  // extern "C"

@@ -27,10 +27,9 @@ def compute_mf_results(training_dataset, testing_dataset, synthetic_data=None, n
     masked = metrics.mask_training_examples(sparse_training_set=training_data, dense_matrix=recon[:training_data.shape[0]].copy())
     lo = head.shape[0]
     block = masked[lo: lo + valid_data.shape[0]]
-    recall, ndcg = [], []
-    for k in K_LIST:
-        recall.append(np.round(np.nanmean(metrics.recall_at_k_batch(block, valid_data, k=k)), 4))
-        ndcg.append(np.round(np.nanmean(metrics.NDCG_binary_at_k_batch(block, valid_data, k=k)), 4))
+    both = metrics.recall_ndcg_multi_k(block, valid_data, K_LIST)   # one pass over the scores for all six cut-offs
+    recall = [np.round(np.nanmean(both[k][0]), 4) for k in K_LIST]
+    ndcg = [np.round(np.nanmean(both[k][1]), 4) for k in K_LIST]
     return np.array(recall), np.array(ndcg)
 
 

@@ -55,6 +55,33 @@ def _counters(X_pred, heldout, k):
     return hits.cpu().numpy(), nrel.cpu().numpy(), dcg.cpu().numpy()
 
 
+def recall_ndcg_multi_k(X_pred, heldout_batch, ks):
+    """Recall@k and NDCG@k for every k in `ks` from ONE pass over the score matrix: the sorted top-max(ks)
+    list of K3 contains the top-k list of every smaller k, so the six evaluator cut-offs (svd_benchmark.py:57-68) cost one
+    read of the scores instead of twelve.  Returns {k: (recall[rows], ndcg[rows])}, values identical to the per-k calls."""
+    held, stored = _to_device_heldout(heldout_batch)
+    scores = _to_device_scores(X_pred)
+    kmax = max(ks)
+    idx = topk_device(scores, kmax)
+    rows, n_items = held.shape
+    lib = _lib.load()
+    out = {}
+    for k in ks:
+        hits = torch.empty(rows, dtype=torch.int32, device=held.device)
+        nrel = torch.empty(rows, dtype=torch.int32, device=held.device)
+        dcg = torch.empty(rows, dtype=torch.float64, device=held.device)
+        _lib.check(lib.sdrm_recall_ndcg_at_k(_lib.ptr(idx), kmax, k, _lib.ptr(held), rows, n_items, held.stride(0),
+                                             _lib.ptr(hits), _lib.ptr(nrel), _lib.ptr(dcg), _lib.stream_ptr()),
+                   "sdrm_recall_ndcg_at_k")
+        hits, nrel, dcg = hits.cpu().numpy(), nrel.cpu().numpy(), dcg.cpu().numpy()
+        tp = 1.0 / np.log2(np.arange(2, k + 2))
+        cnt = nrel if stored is None else np.asarray(stored)
+        idcg = np.array([tp[: min(int(n), k)].sum() for n in cnt])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            out[k] = (hits.astype(np.float32) / np.minimum(k, nrel.astype(np.int64)), dcg / idcg)
+    return out
+
+
 def recall_at_k_device(X_pred, heldout, k):
     """Both arguments are CUDA tensors [rows, I]; returns float64 ndarray[rows] (0/0 -> NaN like the reference)."""
     hits, nrel, _ = _counters(X_pred, heldout, k)

@@ -91,3 +91,19 @@ def test_topk_full_scale_properties():
     assert bool(((x > kth).sum(dim=1) == 49).all())                        # exactly k-1 elements beat the k-th
     torch_idx = torch.topk(x, 50, dim=1).indices
     assert bool((torch.sort(torch_idx, dim=1).values == torch.sort(idx.long(), dim=1).values).all())
+
+
+def test_multi_k_single_pass_equals_per_k_calls():
+    """One top-50 pass serves all six evaluator cut-offs: values identical to the per-k entry points."""
+    from scipy.sparse import csr_matrix
+    from sdrm_b200 import metrics
+    rng = np.random.RandomState(9)
+    x = np.round(rng.randn(95, 1008) * 8) / 8          # float64 SVD-like scores with ties
+    x[rng.rand(95, 1008) < 0.05] = -np.inf
+    held = csr_matrix((rng.rand(95, 1008) < 0.03).astype(np.float64))
+    ks = [1, 3, 5, 10, 20, 50]
+    both = metrics.recall_ndcg_multi_k(x, held, ks)
+    for k in ks:
+        r, n = metrics.recall_at_k_batch(x, held, k=k), metrics.NDCG_binary_at_k_batch(x, held, k=k)
+        assert np.array_equal(both[k][0], r, equal_nan=True)
+        assert np.array_equal(both[k][1], n, equal_nan=True)

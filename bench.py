@@ -285,7 +285,7 @@ def run_ours(args, w, rank, world, local_rank):
                     "hbm_min_bytes_per_user": 4 * w["I"],
                     "hbm_frac_of_logits_write": (4 * w["I"] * n / (kernel_ms * 1e-3) / 1e9) / peaks["hbm"]}
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:   # reported on rank 0 at N=1 only
             threads = os.cpu_count() or 1
             rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / F)))
             rate, dt = cpu_reference_rate(w, rows, threads)

@@ -363,9 +363,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     setmaxnreg_inc<REGS_EPI>();
     const uint64_t pol_keep = l2_policy_evict_last();
     const int q = warp & 3;
-    const int sub = warp >> 2;
+    int sub = warp >> 2;
     const int r = q * 32 + lane;
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t lane0 = (lane == 0) ? 1u : 0u;
+    pin_reg(lane0); pin_reg(lane_addr);
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
     const uint32_t swz = static_cast<uint32_t>(r & 6) << 4;   // 128-byte swizzle of the row, 32-byte-sector part
     const bool flip = r & 1;                                  // odd rows hold the two 16-byte pieces of a sector swapped
@@ -536,6 +538,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
+          if (c > 0 && publishes) {
+            // Deferred publication of the PREVIOUS chunk (same layer): its stores were issued a whole accumulator wait ago, so
+            // the membar inside fence.proxy.async returns at once instead of costing an L2 round trip per chunk (ncu: 8 % of
+            // the epilogue warps' time).  (Issued before the TMEM load: with the accumulator registers live across the fence
+            // ptxas spills.)  Only the next layer reads
+            // these activations, and it cannot start before this layer's last chunk, which is published immediately below.
+            fence_proxy_async();
+            __syncwarp();
+            if (lane0) mbar_arrive(bar_act_chunk(c - 1));
+            SDRM_TR_EPI(5);
+          }
           if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
           const float4* bs = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll 1
@@ -632,23 +645,23 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) {
+          if (lane0) {
             if (PAIR) mbar_arrive_cluster(mapa_cluster(bar_acc_empty(buf), leader_rank));   // the leader CTA issues the UMMAs
             else mbar_arrive(bar_acc_empty(buf));
           }
           SDRM_TR_EPI(3);
           ++cc;
-          // publish this chunk's activations to the TMA (async) proxy and tell the A producer
-          if (publishes) {
+          // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
+          if (publishes && c == NCH - 1) {
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_act_chunk(c));
+            if (lane0) mbar_arrive(bar_act_chunk(c));
             SDRM_TR_EPI(5);
           }
         }
         if (KIND == EPI_POSTERIOR && step > 1) {
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_state_ready);   // x_{i-1} is complete: the noise warps may prepare step i-1
+          if (lane0) mbar_arrive(bar_state_ready);   // x_{i-1} is complete: the noise warps may prepare step i-1
         }
       };
       auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf) {

@@ -278,10 +278,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // small math
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fast_tanh(float x) {
-  // tanh(x) = 1 - 2 / (exp(2x) + 1); ex2.approx + rcp.approx, abs error ~1e-7, saturates cleanly
-  float e = exp2f(x * 2.885390081777927f);  // 2*log2(e)
-  return 1.0f - 2.0f * __frcp_rn(e + 1.0f);
+  // tanh(x) = 1 - 2 / (exp(2x) + 1) on two MUFU ops (ex2.approx, rcp.approx: no Newton step, no slow path), abs error ~3e-7,
+  // saturates cleanly (e = inf -> r = 0 -> 1;  e = 0 -> r = 1 -> -1)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.885390081777927f));   // 2*log2(e)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
 }
+// keep a loop-invariant value in its register: without this ptxas re-derives thread-index based values with S2R
+// (a ~20-cycle short-scoreboard stall) inside the hottest loops
+__device__ __forceinline__ void pin_reg(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void pin_reg(int& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

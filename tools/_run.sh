@@ -1,1 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --rows 37888 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; cat gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+timeout 600 python -m pytest tests/test_sampler_gpu.py tests/test_probe_gpu.py -x -q 2>&1 | tail -3
+bash tools/quick_bench.sh 37888 "2:37888 2:256 1:18944"

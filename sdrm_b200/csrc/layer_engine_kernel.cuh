@@ -35,6 +35,11 @@
 #ifndef SDRM_NSTG_PAIR
 #define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 measured no faster and leaves no room for the bias slices
 #endif
+#ifdef SDRM_EXPERIMENT_NO_FENCE   // timing experiment only: results become wrong
+#define SDRM_EPI_FENCE() do { } while (0)
+#else
+#define SDRM_EPI_FENCE() fence_proxy_async()
+#endif
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
 #define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
@@ -379,8 +384,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // (the stores scatter over 32 rows per warp, so their count is what costs)
     auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
       uint8_t* sector = buf_row + static_cast<size_t>(f0 >> 6) * A_TILE_BYTES + ((static_cast<uint32_t>(f0 & 48) << 1) ^ swz);
+#ifdef SDRM_EXPERIMENT_NO_FLIP
+      const uint32_t a0 = pk[0], a1 = pk[1], a2 = pk[2], a3 = pk[3], b0 = pk[4], b1 = pk[5], b2 = pk[6], b3 = pk[7];
+#else
       const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
       const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
+#endif
       asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
                    ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol_keep)
                    : "memory");
@@ -519,7 +528,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           __syncwarp();                                             // every lane is done with the previous chunk's slice
           *reinterpret_cast<float2*>(bias_s + 2 * lane) = bnext;
           __syncwarp();
-          if (c + 1 < NCH) bnext = fetch_slice(c + 1);
           // Software pipeline over this warp's groups: the TMEM load (and, for the posterior update, the state columns and
           // keep bits) of group g+4 is requested as soon as group g has consumed its own, so its latency hides behind the
           // arithmetic and the store of group g.
@@ -533,7 +541,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               if (step > 1) keep = mask_row[g16];
             }
           };
-          if (KIND == EPI_POSTERIOR && sub < ngroups) request_state(sub);   // does not depend on the accumulator: ask before waiting
+          // does not depend on the accumulator: ask before waiting (first chunk only: later chunks fence first, and a membar
+          // would wait for these loads to return)
+          if (KIND == EPI_POSTERIOR && c == 0 && sub < ngroups) request_state(sub);
           SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
@@ -544,11 +554,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             // the epilogue warps' time).  (Issued before the TMEM load: with the accumulator registers live across the fence
             // ptxas spills.)  Only the next layer reads
             // these activations, and it cannot start before this layer's last chunk, which is published immediately below.
-            fence_proxy_async();
+            SDRM_EPI_FENCE();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c - 1));
             SDRM_TR_EPI(5);
           }
+          if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
+          if (KIND == EPI_POSTERIOR && c > 0 && sub < ngroups) request_state(sub);
           if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
           const float4* bs = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll 1
@@ -653,7 +665,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           ++cc;
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           if (publishes && c == NCH - 1) {
-            fence_proxy_async();
+            SDRM_EPI_FENCE();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c));
             SDRM_TR_EPI(5);

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_sampler_gpu.py tests/test_probe_gpu.py -x -q 2>&1 | tail -3
-bash tools/quick_bench.sh 37888 "2:37888 2:256 1:18944"
+rm -f gpurun_out/e2e_ours_ml100k.jsonl
+timeout 1500 python tools/our_e2e.py 5 1 gpurun_out/e2e_ours_ml100k.jsonl 2>&1 | tail -8

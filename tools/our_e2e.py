@@ -28,13 +28,21 @@ for run in range(runs):
     torch.cuda.synchronize()
     res = {"impl": "sdrm_b200", "run": run, "train_s": round(time.time() - t0, 1), "only_synthetic": only_synth}
     t1 = time.time()
-    M = sample_ddpm(N_USERS, DIFF, VAE, A["L"], A["nd"], timesteps="random", n_timesteps=A["T"]).detach().cpu().numpy()
-    res["sample_random_s"] = round(time.time() - t1, 4); t1 = time.time()
-    F = sample_ddpm(N_USERS, DIFF, VAE, A["L"], A["nd"], n_timesteps=A["T"]).detach().cpu().numpy()
-    res["sample_full_s"] = round(time.time() - t1, 4)
+    from sdrm_b200.sparsify import equal_sparsity_device
+    M = sample_ddpm(N_USERS, DIFF, VAE, A["L"], A["nd"], timesteps="random", n_timesteps=A["T"])
+    torch.cuda.synchronize(); res["sample_random_s"] = round(time.time() - t1, 4); t1 = time.time()
+    F = sample_ddpm(N_USERS, DIFF, VAE, A["L"], A["nd"], n_timesteps=A["T"])
+    torch.cuda.synchronize(); res["sample_full_s"] = round(time.time() - t1, 4)
     V = VAE.sample(N_USERS)
     for name, S in (("F-SDRM", F), ("M-SDRM", M), ("MultiVAE++", V)):
-        syn = pd.DataFrame((S >= np.quantile(S.flatten(), SPARSITY)).astype(int))
+        if isinstance(S, torch.Tensor):   # K4: threshold identical to np.quantile, 1 bit per entry to the host
+            pm = equal_sparsity_device(S, SPARSITY)
+            dense = pm.numpy(int)
+            host = S.cpu().numpy()
+            assert pm.threshold == np.quantile(host.flatten(), SPARSITY) and (dense == (host >= pm.threshold)).all()
+            syn = pd.DataFrame(dense)
+        else:
+            syn = pd.DataFrame((S >= np.quantile(S.flatten(), SPARSITY)).astype(int))
         rec, ndcg = evaluators.compute_mf_results(TRAIN, VALID, synthetic_data=syn, nnmf=False, only_synthetic=only_synth)
         res[name] = {"recall@10": float(rec[3]), "ndcg@10": float(ndcg[3])}
     print(json.dumps(res), flush=True)

@@ -35,11 +35,6 @@
 #ifndef SDRM_NSTG_PAIR
 #define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 measured no faster and leaves no room for the bias slices
 #endif
-#ifdef SDRM_EXPERIMENT_NO_FENCE   // timing experiment only: results become wrong
-#define SDRM_EPI_FENCE() do { } while (0)
-#else
-#define SDRM_EPI_FENCE() fence_proxy_async()
-#endif
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
 #define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
@@ -384,12 +379,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // (the stores scatter over 32 rows per warp, so their count is what costs)
     auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
       uint8_t* sector = buf_row + static_cast<size_t>(f0 >> 6) * A_TILE_BYTES + ((static_cast<uint32_t>(f0 & 48) << 1) ^ swz);
-#ifdef SDRM_EXPERIMENT_NO_FLIP
-      const uint32_t a0 = pk[0], a1 = pk[1], a2 = pk[2], a3 = pk[3], b0 = pk[4], b1 = pk[5], b2 = pk[6], b3 = pk[7];
-#else
       const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
       const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
-#endif
       asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
                    ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol_keep)
                    : "memory");
@@ -554,7 +545,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             // the epilogue warps' time).  (Issued before the TMEM load: with the accumulator registers live across the fence
             // ptxas spills.)  Only the next layer reads
             // these activations, and it cannot start before this layer's last chunk, which is published immediately below.
-            SDRM_EPI_FENCE();
+            fence_proxy_async();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c - 1));
             SDRM_TR_EPI(5);
@@ -665,7 +656,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           ++cc;
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           if (publishes && c == NCH - 1) {
-            SDRM_EPI_FENCE();
+            fence_proxy_async();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c));
             SDRM_TR_EPI(5);

@@ -128,3 +128,30 @@ def test_empty_and_ragged():
     out = eng.sample(n, seed=1, check=True)
     assert out.shape == (1, I) and torch.isfinite(out).all()
     assert eng.sample(0).shape == (0, I)
+
+
+def test_headline_config_rows_match_oracle_at_full_scale():
+    """BASELINE.json's scale-up configuration itself (T=178, L=950, H=1000, nh=4, I=20 000) on two full waves of CTA pairs:
+    rows taken from the first, a middle and the ragged last tile of a 37 900-row launch are compared with the oracle over
+    the WHOLE 178-step chain, and the launch is checked for determinism and sharding invariance."""
+    from oracle import philox_ref
+    from oracle import sdrm_oracle as orc
+    n, I, H, L, T, nh, nd = 37900, 20000, 1000, 950, 178, 4, 1.0
+    diff, vae = random_modules(I, H, L, T, nh, seed=11, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    seed, row_offset = 0xC0FFEE1234, 5_000_000_000          # row ids beyond 2^32 exercise the high counter word
+    out = eng.sample(n, row_offset=row_offset, seed=seed, check=True)
+    assert torch.isfinite(out).all()
+    again = eng.sample(n, row_offset=row_offset, seed=seed, check=True)
+    assert torch.equal(out, again)                            # deterministic
+    lo = 19000
+    shard = eng.sample(700, row_offset=row_offset + lo, seed=seed, check=True)
+    assert torch.equal(shard, out[lo:lo + 700])               # rows depend only on (seed, global row id)
+    dsd, vsd = state_dicts(diff, vae)
+    for start in (0, 18944 + 37, n - 12):                     # first tile, second wave, ragged last tile
+        rows = 12
+        xT, z, keep = philox_ref.sampler_noise(seed, row_offset + start, rows, L, T)
+        ref = orc.sample_full(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep))
+        got = out[start:start + rows].cpu()
+        assert rel_fro(got, ref) < TOL, (start, rel_fro(got, ref))
+        assert max_scaled_err(got, ref) < TOL_MAX

@@ -367,7 +367,7 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
   if (T < 1 || L < 1 || D < 1 || nh < 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_denoiser_pack: bad shape");
   if (2 + nh > MAX_STEP_LAYERS) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: nh > 6");
   if (L > MAX_ACT_CHUNKS * MAX_NC || D > MAX_ACT_CHUNKS * MAX_NC)
-    return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: latent / hidden width above 2048");
+    return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_denoiser_pack: latent / hidden width above 8 x 256");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
   const bool same = h->have_den && h->T == T && h->L == L && h->D == D && h->nh == nh;
@@ -405,7 +405,7 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
                       int L, int H, int I, void* stream) {
   if (!h || !d_W1 || !d_b1 || !d_W2 || !d_b2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: null pointer");
   if (L < 1 || H < 1 || I < 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_decoder_pack: bad shape");
-  if (H > MAX_ACT_CHUNKS * MAX_NC) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_decoder_pack: VAE hidden width above 2048");
+  if (H > MAX_ACT_CHUNKS * MAX_NC) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_decoder_pack: VAE hidden width above 8 x 256");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
   const bool same = h->have_dec && h->g1.K == L && h->H == H && h->I == I;

@@ -9,13 +9,16 @@ namespace sdrm {
 constexpr int TILE_M = 128;                        // rows of users per CTA tile (UMMA M)
 constexpr int KBLK = 64;                           // bf16 elements per 128-byte swizzle row
 constexpr int A_TILE_BYTES = TILE_M * 128;         // one activation k-block image: 128 rows x 128 B
-constexpr int MAX_NC = 256;                        // widest UMMA N
+#ifndef SDRM_MAX_NC
+#define SDRM_MAX_NC 256   // widest UMMA N.  240 would shrink a pair-mode stage to 31 KB and fit 7 stages, but measured
+#endif                    // slower (81.4 vs 79.8 ms for two waves at cfg 5): the decoder then needs 84 instead of 79 chunks
+constexpr int MAX_NC = SDRM_MAX_NC;
 constexpr int W_TILE_BYTES_MAX = MAX_NC * 128;     // one weight k-block image
 constexpr int STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES_MAX;
 constexpr int NUM_STAGES = 4;
 constexpr int MAX_STEP_LAYERS = 8;                 // 2 + nh, nh <= 6
 constexpr int NUM_ACT_BUFS = 4;
-constexpr int MAX_ACT_CHUNKS = 8;                  // N chunks of an activation-producing layer (features <= 2048)
+constexpr int MAX_ACT_CHUNKS = 8;                  // N chunks of an activation-producing layer (features <= 8 * MAX_NC)
 constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
 constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;

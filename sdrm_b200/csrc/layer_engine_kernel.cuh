@@ -33,7 +33,7 @@
 #define SDRM_TR_EPI(code) do { } while (0)
 #endif
 #ifndef SDRM_NSTG_PAIR
-#define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 measured no faster and leaves no room for the bias slices
+#define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 (with 31 KB stages, MAX_NC = 240) measured no faster
 #endif
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr bool PAIR = CS >= 2;
   constexpr int NPAIRS = PAIR ? CS / 2 : 1;
   constexpr int NSTG = PAIR ? SDRM_NSTG_PAIR : 4;
-  constexpr uint32_t W_STAGE_BYTES = PAIR ? 16384u : 32768u;
+  constexpr uint32_t W_STAGE_BYTES = PAIR ? static_cast<uint32_t>(MAX_NC / 2 * 128) : static_cast<uint32_t>(MAX_NC * 128);
+  static_assert((A_TILE_BYTES + W_STAGE_BYTES) % 1024 == 0, "stages stay 1024-byte aligned (SWIZZLE_128B operand atoms)");
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = CS;
   constexpr uint32_t BIAS_SLICE_BYTES = 4 * 16 * 4;   // per epilogue warp: the bias of its (at most 4) column groups of one chunk
@@ -539,12 +540,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          if (c > 0 && publishes) {
+          if (c > 0 && c < NCH - 1 && publishes) {   // chunk c-1 <= NCH-3
             // Deferred publication of the PREVIOUS chunk (same layer): its stores were issued a whole accumulator wait ago, so
-            // the membar inside fence.proxy.async returns at once instead of costing an L2 round trip per chunk (ncu: 8 % of
-            // the epilogue warps' time).  (Issued before the TMEM load: with the accumulator registers live across the fence
-            // ptxas spills.)  Only the next layer reads
-            // these activations, and it cannot start before this layer's last chunk, which is published immediately below.
+            // the membar inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only
+            // the next layer reads these activations and it cannot finish its first chunk before this layer's last one.
+            // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The LAST
+            // chunk's epilogue is the critical path of the layer boundary (timeline: the next layer's first chunk takes twice
+            // as long as the others), so nothing is deferred into it.
             fence_proxy_async();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c - 1));
@@ -655,7 +657,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           SDRM_TR_EPI(3);
           ++cc;
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
-          if (publishes && c == NCH - 1) {
+          // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
+          // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
+          if (publishes && c >= NCH - 2) {
             fence_proxy_async();
             __syncwarp();
             if (lane0) mbar_arrive(bar_act_chunk(c));

@@ -153,6 +153,47 @@ __global__ void __launch_bounds__(256) loss_seeds_kernel(const float* __restrict
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// First encoder layer of the frozen VAE on CSR rows (reference: VAE.encode in eval,
+// train_SDRM.py:241-250, fed by `x.to_dense()` at train_SDRM.py:323):
+//   hidden[r] = tanh( W_e1 (x_r / max(||x_r||_2, 1e-12)) + b_e1 )
+// For a sparse interaction row this is a gather-sum of nnz(r) rows of W_e1^T (an embedding bag); the dense [B, I]
+// batch of the reference (29 MB per step at adm, 80 GB for the scale-up shape) is never materialised.
+// One CTA per row; thread t owns hidden columns t, t + 256, ...; every gathered weight row is read coalesced.
+// ------------------------------------------------------------------------------------------------
+constexpr int ENC_THREADS = 256;
+constexpr int ENC_MAX_PER_THREAD = 8;   // H <= 2048
+__global__ void __launch_bounds__(ENC_THREADS) encode_csr_kernel(const long long* __restrict__ indptr, const long long* __restrict__ indices,
+                                                                 const float* __restrict__ values, int n_items,
+                                                                 const float* __restrict__ W1T, const float* __restrict__ b1, int H,
+                                                                 float* __restrict__ hidden) {
+  const long long r = blockIdx.x;
+  const long long lo = indptr[r], hi = indptr[r + 1];
+  float acc[ENC_MAX_PER_THREAD];
+#pragma unroll
+  for (int u = 0; u < ENC_MAX_PER_THREAD; ++u) acc[u] = 0.0f;
+  float ss = 0.0f;
+  for (long long p = lo; p < hi; ++p) {
+    const long long j = __ldg(indices + p);
+    const float v = __ldg(values + p);
+    ss = fmaf(v, v, ss);
+    if (j < 0 || j >= n_items) continue;   // malformed index: ignored rather than read out of bounds
+    const float* w = W1T + j * H;
+#pragma unroll
+    for (int u = 0; u < ENC_MAX_PER_THREAD; ++u) {
+      const int h = threadIdx.x + u * ENC_THREADS;
+      if (h < H) acc[u] = fmaf(v, __ldg(w + h), acc[u]);
+    }
+  }
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // F.normalize(x, p=2, dim=1)
+#pragma unroll
+  for (int u = 0; u < ENC_MAX_PER_THREAD; ++u) {
+    const int h = threadIdx.x + u * ENC_THREADS;
+    if (h < H) hidden[r * H + h] = tanhf(fmaf(acc[u], inv, b1[h]));
+  }
+}
+
 }  // namespace sdrm
 
 using namespace sdrm;
@@ -202,6 +243,20 @@ int sdrm_loss_grad_seeds(const float* d_pred, const float* d_sx, const float* d_
   if (count <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_loss_grad_seeds: count <= 0");
   loss_seeds_kernel<<<grid_for(count), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_pred, d_sx, d_psx, d_mu, count, static_cast<float>(mu_coef * mu_coef), d_stats, d_g_pred, d_g_sx, d_g_psx, d_loss_out);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+
+int sdrm_encode_csr(const int64_t* d_indptr, const int64_t* d_indices, const float* d_values, int64_t rows, int n_items,
+                    const float* d_W1T, const float* d_b1, int H, float* d_hidden, void* stream) {
+  if (!d_indptr || !d_W1T || !d_b1 || !d_hidden) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_encode_csr: null pointer");
+  if (rows < 0 || n_items < 1 || H < 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_encode_csr: bad shape");
+  if (H > ENC_THREADS * ENC_MAX_PER_THREAD) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_encode_csr: hidden width above 2048");
+  if (rows == 0) return SDRM_OK;
+  encode_csr_kernel<<<static_cast<unsigned>(rows), ENC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(d_indptr), reinterpret_cast<const long long*>(d_indices), d_values, n_items, d_W1T, d_b1, H,
+      d_hidden);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
 }

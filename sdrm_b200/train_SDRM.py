@@ -309,6 +309,7 @@ def train_SDRM(dl, N_ITEMS, VAE_HIDDEN, VAE_LATENT, VAE_BATCH_SIZE, VAE_LR, DIFF
     DIFF.train()
     diff_optim = torch.optim.Adam(DIFF.parameters(), lr=DIFF_LR, weight_decay=0.0001, eps=1e-8)
     stepper = training.DiffusionTrainStep(DIFF, ab_t, TIMESTEPS, noise_divider)
+    encoder = training.FrozenEncoder(variational_ae)   # sparse rows -> mu without densifying the batch (train_SDRM.py:323-324)
 
     start_time = time.time()
     for ep in range(DIFF_TRAINING_EPOCHS):
@@ -317,8 +318,7 @@ def train_SDRM(dl, N_ITEMS, VAE_HIDDEN, VAE_LATENT, VAE_BATCH_SIZE, VAE_LR, DIFF
         diff_optim.param_groups[0]["lr"] = DIFF_LR * (1 - ep / DIFF_TRAINING_EPOCHS)
         for x, _ in iter(dl):
             diff_optim.zero_grad()
-            with torch.no_grad():
-                encode_x, _ = variational_ae.encode(x.to_dense().to(dev))
+            encode_x = encoder(x)
             loss = stepper.loss(encode_x)
             loss.backward()
             diff_optim.step()

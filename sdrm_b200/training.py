@@ -48,6 +48,54 @@ class CudaLossBackend:
         return g[0], g[1], g[2], loss
 
 
+class FrozenEncoder:
+    """mu = VAE.encode(x)[0] of the FROZEN, eval-mode VAE for sparse interaction batches (train_SDRM.py:291-294, 323-324).
+
+    The reference densifies every minibatch (`x.to_dense()`: [B, I] floats, 29 MB per step at adm) and runs the first
+    encoder Linear as a dense GEMM over mostly-zero columns.  Here the first layer is kernel `sdrm_encode_csr` (gather-sum
+    of the row's items over W_e1^T, L2-normalisation and tanh fused); the small second layer [B, H] x [H, L] stays a library
+    GEMM and only its mu half is computed (logvar and the KL term are discarded by the caller, is_training == 0).
+    The reference's eval-mode encode also draws an unused randn_like(std); that RNG side effect is not reproduced.
+    """
+
+    def __init__(self, vae):
+        self.lib = _lib.load()
+        lin1, lin2 = vae.encoder[0], vae.encoder[2]
+        L = vae.latent_dim
+        self.n_items, self.H, self.L = lin1.weight.shape[1], lin1.weight.shape[0], L
+        self.W1T = lin1.weight.detach().t().contiguous().float()      # [I, H]; the VAE is frozen: transposed once
+        self.b1 = lin1.bias.detach().contiguous().float()
+        self.W2mu = lin2.weight.detach()[:L].t().contiguous().float() # [H, L]
+        self.b2mu = lin2.bias.detach()[:L].contiguous().float()
+
+    def hidden(self, x):
+        dev = self.W1T.device
+        if dev.type != "cuda":
+            raise _lib.SdrmError("FrozenEncoder: the VAE must live on a CUDA device (no CPU fallback)")
+        if x.layout == torch.sparse_csr:
+            csr = x
+        elif x.layout == torch.sparse_coo:
+            csr = x.coalesce().to_sparse_csr()
+        else:
+            csr = x.to_sparse_csr()
+        csr = csr.to(dev)
+        if csr.shape[1] != self.n_items:
+            raise ValueError(f"batch has {csr.shape[1]} items, the encoder expects {self.n_items}")
+        indptr = csr.crow_indices().to(torch.int64).contiguous()
+        indices = csr.col_indices().to(torch.int64).contiguous()
+        values = csr.values().to(torch.float32).contiguous()
+        rows = csr.shape[0]
+        out = torch.empty((rows, self.H), dtype=torch.float32, device=dev)
+        _lib.check(self.lib.sdrm_encode_csr(_lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values), rows, self.n_items,
+                                            _lib.ptr(self.W1T), _lib.ptr(self.b1), self.H, _lib.ptr(out), _lib.stream_ptr()),
+                   "sdrm_encode_csr")
+        return out
+
+    @torch.no_grad()
+    def __call__(self, x):
+        return torch.addmm(self.b2mu, self.hidden(x), self.W2mu)
+
+
 class ScoreMatchingLoss(torch.autograd.Function):
     """loss = 0.5 (mean((sd-r)^2) + mean((r-sx)^2)) / (1e-8 + var(r)),  r = pred - mu, sd = (psx - sx)/mu_coef^2,
     with means / variance over the GLOBAL batch when `group` is a process group."""

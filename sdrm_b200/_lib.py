@@ -39,6 +39,8 @@ SIGNATURES = {
                                     _P, _P, _P, _P, _P, _P, _P, _P]),
     "sdrm_loss_stats": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, _P, _P]),
     "sdrm_encode_csr": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.c_int, _P, _P]),
+    "sdrm_multinomial_nll_fwd": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, _P]),
+    "sdrm_multinomial_nll_bwd": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int64, C.c_int64, _P, _P, _P, C.c_float, _P, C.c_int64, _P]),
     "sdrm_key_histogram": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.c_int, _P, _P]),
     "sdrm_threshold_pack": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_double, C.c_int, _P, C.c_int64, _P, _P]),
     "sdrm_loss_grad_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, _P, _P, _P, _P, _P, _P]),

@@ -2,6 +2,7 @@
 // perturb_input 202-203, score_matching_loss 191-199).  All three are HBM-bound streaming kernels:
 // vectorised (float4) coalesced reads, one pass, fp64 block reductions for the loss statistics.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/sdrm_b200.h"
@@ -194,6 +195,110 @@ __global__ void __launch_bounds__(ENC_THREADS) encode_csr_kernel(const long long
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Multinomial negative log-likelihood of the MultiVAE++ training step (reference
+// train_SDRM.py:143: neg_ll = -mean_r( sum_j log_softmax(output)[r, j] * X[r, j] )).
+// Forward: ONE pass over the logits and the interaction rows (8 bytes per entry) with an online softmax gives, per row,
+//   lse = log sum_j exp(o_j),  sx = sum_j X_j,  dot = sum_j X_j o_j      (loss_r = -(dot - sx * lse))
+// Backward: one pass writes d loss / d o_j = scale * (softmax_j * sx - X_j)  (12 bytes per entry), scale = grad / rows.
+// One CTA per row, float4 loads when the rows are 16-byte aligned.
+// ------------------------------------------------------------------------------------------------
+constexpr int NLL_THREADS = 256;
+
+__device__ __forceinline__ void online_add(float& m, float& s, float v) {
+  if (v > m) { s = s * __expf(m - v) + 1.0f; m = v; }
+  else s += __expf(v - m);
+}
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mm = fmaxf(m, m2);
+  s = (m == -INFINITY ? 0.0f : s * __expf(m - mm)) + (m2 == -INFINITY ? 0.0f : s2 * __expf(m2 - mm));
+  m = mm;
+}
+
+__global__ void __launch_bounds__(NLL_THREADS) nll_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ X, int n_items,
+                                                              long long ld_o, long long ld_x, float* __restrict__ row_lse,
+                                                              float* __restrict__ row_sx, float* __restrict__ row_dot) {
+  const long long r = blockIdx.x;
+  const float* o = logits + r * ld_o;
+  const float* x = X + r * ld_x;
+  float m = -INFINITY, s = 0.0f, sx = 0.0f, dot = 0.0f;
+  const bool vec = ((ld_o & 3) == 0) && ((ld_x & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  int j0 = 0;
+  if (vec) {
+    const int n4 = n_items >> 2;
+    for (int j = threadIdx.x; j < n4; j += NLL_THREADS) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(o) + j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x) + j);
+      online_add(m, s, a.x); online_add(m, s, a.y); online_add(m, s, a.z); online_add(m, s, a.w);
+      sx += (b.x + b.y) + (b.z + b.w);
+      dot = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, dot))));
+    }
+    j0 = n4 << 2;
+  }
+  for (int j = j0 + threadIdx.x; j < n_items; j += NLL_THREADS) {
+    const float a = __ldg(o + j), b = __ldg(x + j);
+    online_add(m, s, a);
+    sx += b;
+    dot = fmaf(a, b, dot);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, off), __shfl_xor_sync(0xffffffffu, s, off));
+    sx += __shfl_xor_sync(0xffffffffu, sx, off);
+    dot += __shfl_xor_sync(0xffffffffu, dot, off);
+  }
+  __shared__ float sh[4][NLL_THREADS / 32];
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { sh[0][w] = m; sh[1][w] = s; sh[2][w] = sx; sh[3][w] = dot; }
+  __syncthreads();
+  if (w == 0) {
+    m = l < NLL_THREADS / 32 ? sh[0][l] : -INFINITY;
+    s = l < NLL_THREADS / 32 ? sh[1][l] : 0.0f;
+    sx = l < NLL_THREADS / 32 ? sh[2][l] : 0.0f;
+    dot = l < NLL_THREADS / 32 ? sh[3][l] : 0.0f;
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) {
+      online_merge(m, s, __shfl_xor_sync(0xffffffffu, m, off), __shfl_xor_sync(0xffffffffu, s, off));
+      sx += __shfl_xor_sync(0xffffffffu, sx, off);
+      dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    }
+    if (l == 0) { row_lse[r] = m + logf(s); row_sx[r] = sx; row_dot[r] = dot; }
+  }
+}
+
+__global__ void __launch_bounds__(NLL_THREADS) nll_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ X, int n_items,
+                                                              long long ld_o, long long ld_x, const float* __restrict__ row_lse,
+                                                              const float* __restrict__ row_sx, const float* __restrict__ scale_ptr,
+                                                              float scale_mul, float* __restrict__ grad, long long ld_g) {
+  const long long r = blockIdx.x;
+  const float* o = logits + r * ld_o;
+  const float* x = X + r * ld_x;
+  float* g = grad + r * ld_g;
+  const float lse = row_lse[r], sx = row_sx[r];
+  const float scale = (scale_ptr ? __ldg(scale_ptr) : 1.0f) * scale_mul;
+  const bool vec = ((ld_o & 3) == 0) && ((ld_x & 3) == 0) && ((ld_g & 3) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(grad) & 15) == 0);
+  int j0 = 0;
+  if (vec) {
+    const int n4 = n_items >> 2;
+    for (int j = threadIdx.x; j < n4; j += NLL_THREADS) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(o) + j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(x) + j);
+      float4 d;
+      d.x = scale * fmaf(__expf(a.x - lse), sx, -b.x);
+      d.y = scale * fmaf(__expf(a.y - lse), sx, -b.y);
+      d.z = scale * fmaf(__expf(a.z - lse), sx, -b.z);
+      d.w = scale * fmaf(__expf(a.w - lse), sx, -b.w);
+      reinterpret_cast<float4*>(g)[j] = d;
+    }
+    j0 = n4 << 2;
+  }
+  for (int j = j0 + threadIdx.x; j < n_items; j += NLL_THREADS)
+    g[j] = scale * fmaf(__expf(__ldg(o + j) - lse), sx, -__ldg(x + j));
+}
+
 }  // namespace sdrm
 
 using namespace sdrm;
@@ -257,6 +362,31 @@ int sdrm_encode_csr(const int64_t* d_indptr, const int64_t* d_indices, const flo
   encode_csr_kernel<<<static_cast<unsigned>(rows), ENC_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const long long*>(d_indptr), reinterpret_cast<const long long*>(d_indices), d_values, n_items, d_W1T, d_b1, H,
       d_hidden);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+
+int sdrm_multinomial_nll_fwd(const float* d_logits, const float* d_x, int64_t rows, int n_items, int64_t ld_logits, int64_t ld_x,
+                             float* d_row_lse, float* d_row_sx, float* d_row_dot, void* stream) {
+  if (!d_logits || !d_x || !d_row_lse || !d_row_sx || !d_row_dot) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_multinomial_nll_fwd: null pointer");
+  if (rows < 0 || n_items < 1 || ld_logits < n_items || ld_x < n_items) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_multinomial_nll_fwd: bad shape");
+  if (rows == 0) return SDRM_OK;
+  nll_fwd_kernel<<<static_cast<unsigned>(rows), NLL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(d_logits, d_x, n_items, ld_logits, ld_x,
+                                                                                                   d_row_lse, d_row_sx, d_row_dot);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_multinomial_nll_bwd(const float* d_logits, const float* d_x, int64_t rows, int n_items, int64_t ld_logits, int64_t ld_x,
+                             const float* d_row_lse, const float* d_row_sx, const float* d_grad_loss, float scale,
+                             float* d_grad_logits, int64_t ld_grad, void* stream) {
+  if (!d_logits || !d_x || !d_row_lse || !d_row_sx || !d_grad_logits) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_multinomial_nll_bwd: null pointer");
+  if (rows < 0 || n_items < 1 || ld_logits < n_items || ld_x < n_items || ld_grad < n_items)
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_multinomial_nll_bwd: bad shape");
+  if (rows == 0) return SDRM_OK;
+  nll_bwd_kernel<<<static_cast<unsigned>(rows), NLL_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logits, d_x, n_items, ld_logits, ld_x, d_row_lse, d_row_sx, d_grad_loss, scale, d_grad_logits, ld_grad);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
 }

@@ -239,7 +239,7 @@ def train_variational_autoencoder(model, train_data, test_data, epochs, batch_si
             X = torch.tensor(train_data[s:e].toarray(), dtype=torch.float32, device=dev)
             optimizer.zero_grad()
             output, vae_kl = model(X)
-            neg_ll = -torch.mean(torch.sum(F.log_softmax(output, dim=1) * X, dim=1))
+            neg_ll = training.multinomial_nll(output, X)   # fused log-softmax NLL (train_SDRM.py:143)
             loss = neg_ll + anneal * vae_kl + model.get_l2_reg()
             losses.append(loss.detach())
             loss.backward()

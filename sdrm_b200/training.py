@@ -48,6 +48,45 @@ class CudaLossBackend:
         return g[0], g[1], g[2], loss
 
 
+class MultinomialNLL(torch.autograd.Function):
+    """neg_ll = -mean_r(sum_j log_softmax(logits)[r, j] * X[r, j])  (reference train_SDRM.py:143, MultiVAE++ training step)
+    as two fused passes (kernels `sdrm_multinomial_nll_fwd/bwd`): the [B, I] log_softmax and its autograd temporaries are
+    never materialised; forward reads logits and X once, backward writes the logits gradient once."""
+
+    @staticmethod
+    def forward(ctx, logits, X):
+        if logits.device.type != "cuda":
+            raise _lib.SdrmError("multinomial_nll: logits must be a CUDA tensor (no CPU fallback)")
+        lib = _lib.load()
+        logits = logits if (logits.dtype == torch.float32 and logits.stride(1) == 1) else logits.float().contiguous()
+        X = X if (X.dtype == torch.float32 and X.stride(1) == 1) else X.float().contiguous()
+        rows, n_items = logits.shape
+        if X.shape != logits.shape:
+            raise ValueError("logits and X must have the same [rows, items] shape")
+        lse, sx, dot = (torch.empty(rows, dtype=torch.float32, device=logits.device) for _ in range(3))
+        _lib.check(lib.sdrm_multinomial_nll_fwd(_lib.ptr(logits), _lib.ptr(X), rows, n_items, logits.stride(0), X.stride(0),
+                                                _lib.ptr(lse), _lib.ptr(sx), _lib.ptr(dot), _lib.stream_ptr()),
+                   "sdrm_multinomial_nll_fwd")
+        ctx.save_for_backward(logits, X, lse, sx)
+        return -(dot - sx * lse).mean()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        logits, X, lse, sx = ctx.saved_tensors
+        lib = _lib.load()
+        rows, n_items = logits.shape
+        grad = torch.empty_like(logits, memory_format=torch.contiguous_format)
+        g = grad_out.detach().to(torch.float32).contiguous()
+        _lib.check(lib.sdrm_multinomial_nll_bwd(_lib.ptr(logits), _lib.ptr(X), rows, n_items, logits.stride(0), X.stride(0),
+                                                _lib.ptr(lse), _lib.ptr(sx), _lib.ptr(g), 1.0 / rows, _lib.ptr(grad),
+                                                grad.stride(0), _lib.stream_ptr()), "sdrm_multinomial_nll_bwd")
+        return grad, None
+
+
+def multinomial_nll(logits, X):
+    return MultinomialNLL.apply(logits, X)
+
+
 class FrozenEncoder:
     """mu = VAE.encode(x)[0] of the FROZEN, eval-mode VAE for sparse interaction batches (train_SDRM.py:291-294, 323-324).
 

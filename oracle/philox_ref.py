@@ -54,18 +54,6 @@ def normals(seed, stream, rows, step, n_cols):
     return out[:, :n_cols]
 
 
-def keep_masks(seed, stream, rows, step, n_cols):
-    """Dropout keep mask block [len(rows), n_cols] (uint8 0/1)."""
-    rows = np.asarray(rows, dtype=np.uint64)
-    ng = (n_cols + 15) // 16
-    cg = np.arange(ng, dtype=np.uint32)[None, :]
-    r_lo = (rows & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None]
-    c3 = (np.uint32(stream) | ((rows >> np.uint64(32)).astype(np.uint32) << np.uint32(8)))[:, None]
-    x, _, _, _ = philox4x32_10(cg, np.uint32(step), r_lo, c3, seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    bits = (x[:, :, None] >> np.arange(16, dtype=np.uint32)[None, None, :]) & np.uint32(1)
-    return bits.reshape(len(rows), ng * 16)[:, :n_cols].astype(np.uint8)
-
-
 def keep_masks128(seed, stream, rows, step, n_cols):
     """Sampler dropout keep mask block [len(rows), n_cols] (uint8 0/1): one Philox call per 128 columns,
     column 128*b + 32*w + j is bit j of output word w (philox_mask128 in philox.cuh)."""
@@ -78,6 +66,39 @@ def keep_masks128(seed, stream, rows, step, n_cols):
     w = np.stack(words, axis=-1)                                   # [rows, nb, 4]
     bits = (w[..., None] >> np.arange(32, dtype=np.uint32)) & np.uint32(1)   # [rows, nb, 4, 32]
     return bits.reshape(len(rows), nb * 128)[:, :n_cols].astype(np.uint8)
+
+
+def _flat_counter(idx):
+    idx = np.asarray(idx, dtype=np.uint64)
+    return (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32), (idx >> np.uint64(32)).astype(np.uint32)
+
+
+def train_normals(seed, row_offset, B, L):
+    """N(0,1) block [B, L] of the training step (noise_inputs_kernel): keyed by the GLOBAL flat element index
+    i = (row_offset + b) * L + f; quad i // 4 is one Philox call, element i takes Box-Muller output i % 4."""
+    i = np.uint64(row_offset) * np.uint64(L) + np.arange(B * L, dtype=np.uint64)
+    q = np.unique(i >> np.uint64(2))
+    c0, c1 = _flat_counter(q)
+    x, y, z, w = philox4x32_10(c0, c1, np.uint32(0), np.uint32(STREAM_TRAIN_NOISE), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    z0, z1 = _box_muller(x, y)
+    z2, z3 = _box_muller(z, w)
+    table = np.stack([z0, z1, z2, z3], axis=-1).reshape(-1)          # indexed by 4 * (q - q[0]) + lane
+    pos = (i - (q[0] << np.uint64(2))).astype(np.int64)
+    return table[pos].reshape(B, L)
+
+
+def train_keep_masks(seed, row_offset, B, L):
+    """The three dropout keep masks of the training step [3, B, L] (uint8): element i = 512 blk + 4 (32 j + l) + e takes
+    bit (4 j + e) of output word k of Philox(c0|c1 = 32 blk + l, c2 = 0, c3 = STREAM_TRAIN_MASK)."""
+    i = np.uint64(row_offset) * np.uint64(L) + np.arange(B * L, dtype=np.uint64)
+    blk = i >> np.uint64(9)
+    within = (i & np.uint64(511)).astype(np.int64)
+    quad, e = within >> 2, within & 3
+    j, lane = quad >> 5, quad & 31
+    c0, c1 = _flat_counter(blk * np.uint64(32) + lane.astype(np.uint64))
+    words = philox4x32_10(c0, c1, np.uint32(0), np.uint32(STREAM_TRAIN_MASK), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    bit = (4 * j + e).astype(np.uint32)
+    return np.stack([((words[k] >> bit) & np.uint32(1)).astype(np.uint8).reshape(B, L) for k in range(3)])
 
 
 def sampler_noise(seed, row_offset, n, L, T):

@@ -7,7 +7,8 @@
 //             step 0 is x_T; step i >= 2 is the z of reverse step i (train_SDRM.py:51,56)
 //   dropout : (sampler, STREAM_MASK) c0 = column / 128, c1 = step, c2 = row, c3 = STREAM_MASK | ...
 //             -> keep bit of column (128*c0 + 32*w + b) is bit b of output word w   (F.dropout p = 0.5, train_SDRM.py:100)
-//             (training step, STREAM_TRAIN_MASK) c0 = column / 16 -> keep bit of column (16*c0 + b) is bit b of word 0
+//             (training step, STREAM_TRAIN_MASK) c0 = column / 16, c1 = 0 -> keep bit of column (16*c0 + b) for the k-th of
+//             the three denoiser inputs is bit b of output word k
 #pragma once
 #include <stdint.h>
 #include <cuda_runtime.h>
@@ -85,31 +86,6 @@ __device__ __forceinline__ void philox_normal4_keys(const PhiloxKeys& K, uint32_
 // sampler dropout stream: 128 keep bits (columns 128*block .. 128*block+127) of (row, step)
 __device__ __forceinline__ u32x4 philox_mask128(const PhiloxKeys& K, uint32_t stream, uint64_t row, uint32_t step, uint32_t block128) {
   return philox4x32_10_keys(block128, step, static_cast<uint32_t>(row), stream | (static_cast<uint32_t>(row >> 32) << 8), K);
-}
-// Box-Muller on 24-bit uniforms: u1 in (0,1], u2 in [0,1)
-__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
-  float u1 = static_cast<float>((a >> 8) + 1u) * 5.9604644775390625e-8f;  // 2^-24
-  float u2 = static_cast<float>(b >> 8) * 5.9604644775390625e-8f;
-  float r = sqrtf(-2.0f * __logf(u1));
-  float s, c;
-  __sincosf(6.283185307179586f * u2, &s, &c);
-  z0 = r * c;
-  z1 = r * s;
-}
-__device__ __forceinline__ void philox_normal4(uint64_t seed, uint32_t stream, uint64_t row, uint32_t step,
-                                               uint32_t col_quad, float (&z)[4]) {
-  u32x4 r = philox4x32_10(col_quad, step, static_cast<uint32_t>(row),
-                          stream | (static_cast<uint32_t>(row >> 32) << 8), static_cast<uint32_t>(seed),
-                          static_cast<uint32_t>(seed >> 32));
-  box_muller(r.x, r.y, z[0], z[1]);
-  box_muller(r.z, r.w, z[2], z[3]);
-}
-__device__ __forceinline__ uint32_t philox_mask16(uint64_t seed, uint32_t stream, uint64_t row, uint32_t step,
-                                                  uint32_t col_group16) {
-  u32x4 r = philox4x32_10(col_group16, step, static_cast<uint32_t>(row),
-                          stream | (static_cast<uint32_t>(row >> 32) << 8), static_cast<uint32_t>(seed),
-                          static_cast<uint32_t>(seed >> 32));
-  return r.x & 0xFFFFu;
 }
 #endif
 

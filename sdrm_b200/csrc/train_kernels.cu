@@ -11,83 +11,116 @@
 
 namespace sdrm {
 
-// One thread = one group of 4 consecutive latent columns of one row.
+// The [B, L] latent batch is walked as ONE flat array (row stride == L), so every access is a 16-byte vector whatever L is
+// (L = 950 rows are only 8-byte aligned).  A warp owns 512 consecutive elements per iteration: lane l handles the four
+// quads j*32 + l (j = 0..3) -> each of its float4 loads / stores is a fully coalesced 512-byte warp access.  Per thread and
+// iteration: four Gaussian Philox calls (4 normals each) and ONE call for the 3 x 16 dropout bits.
 //   noise   = N(0,1) * nd                                  (train_SDRM.py:326)
 //   x_t     = sqrt(ab[t]) * mu + (1 - ab[t]) * noise       (train_SDRM.py:203 -- NOT sqrt on the noise term)
 //   x_p     = mu + mu_coef * noise                          (train_SDRM.py:194)
 //   in_k    = input_k * keep_k * 2                          (F.dropout p=.5 always on, train_SDRM.py:100)
+// Streams, keyed by the GLOBAL flat element index i = (row_offset + b) * L + f (identical for any row sharding):
+//   normals: Philox(c0|c1 = i / 4, c2 = 0, c3 = STREAM_TRAIN_NOISE) -> Box-Muller pairs -> elements 4 (i/4) .. + 3
+//   masks  : element i = 512 blk + 4 (32 j + l) + e;  Philox(c0|c1 = 32 blk + l, c2 = 0, c3 = STREAM_TRAIN_MASK),
+//            keep bit of the k-th denoiser input = bit (4 j + e) of output word k            (oracle/philox_ref.py)
 __global__ void __launch_bounds__(256) noise_inputs_kernel(
     const float* __restrict__ mu, const long long* __restrict__ t, const float* __restrict__ ab, long long B, int L,
     float nd, float mu_coef, unsigned long long seed, long long row_offset, const float* __restrict__ inj_noise,
     const uint8_t* __restrict__ inj_masks, float* __restrict__ noise_out, float* __restrict__ in_pert,
     float* __restrict__ in_clean, float* __restrict__ in_shift, uint8_t* __restrict__ masks_out) {
-  const int groups = (L + 3) >> 2;
-  const long long total = B * groups;
-  const bool vec = (L & 3) == 0;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long b = idx / groups;
-    const int g = static_cast<int>(idx - b * groups);
-    const int f0 = g * 4;
-    const size_t off = static_cast<size_t>(b) * L + f0;
-    const int nvalid = min(4, L - f0);
-    float m[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (vec) {
-      const float4 v = *reinterpret_cast<const float4*>(mu + off);
-      m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
-    } else {
-      for (int e = 0; e < nvalid; ++e) m[e] = mu[off + e];
+  const long long total = B * L;                       // local elements
+  const unsigned long long g0 = static_cast<unsigned long long>(row_offset) * static_cast<unsigned long long>(L);  // global index of local 0
+  // local element 0 may sit anywhere inside a global 512-block / quad: iterate over GLOBAL blocks covering the local range
+  const unsigned long long first_blk = g0 >> 9, last_blk = (g0 + static_cast<unsigned long long>(total) + 511) >> 9;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const PhiloxKeys K = philox_make_keys(seed);
+  const bool aligned = ((g0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(in_pert) & 15) == 0) && ((reinterpret_cast<uintptr_t>(in_clean) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(in_shift) & 15) == 0) && (!noise_out || (reinterpret_cast<uintptr_t>(noise_out) & 15) == 0);
+  for (unsigned long long blk = first_blk + warp; blk < last_blk; blk += n_warps) {
+    uint32_t keep[3] = {0u, 0u, 0u};
+    if (!inj_masks) {
+      const unsigned long long mc = blk * 32ull + lane;
+      const u32x4 m4 = philox4x32_10_keys(static_cast<uint32_t>(mc), static_cast<uint32_t>(mc >> 32), 0u, STREAM_TRAIN_MASK, K);
+      keep[0] = m4.x; keep[1] = m4.y; keep[2] = m4.z;
     }
-    if (inj_noise) {
-      for (int e = 0; e < nvalid; ++e) nz[e] = inj_noise[off + e];
-    } else {
-      float z4[4];
-      philox_normal4(seed, STREAM_TRAIN_NOISE, static_cast<unsigned long long>(row_offset + b), 0u,
-                     static_cast<uint32_t>(g), z4);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) nz[e] = z4[e] * nd;
-    }
-    const float abt = ab[t[b]];
-    const float sa = sqrtf(abt), om = 1.0f - abt;
-    uint32_t keep[3];
+    for (int j = 0; j < 4; ++j) {
+      const unsigned long long gq = blk * 128ull + static_cast<unsigned long long>(j * 32 + lane);   // global quad index
+      const long long i0 = static_cast<long long>(gq * 4ull - g0);                                    // local index of the quad
+      if (i0 + 3 < 0 || i0 >= total) continue;
+      const bool full = aligned && i0 >= 0 && i0 + 3 < total;
+      float m[4] = {0.f, 0.f, 0.f, 0.f}, nz[4] = {0.f, 0.f, 0.f, 0.f};
+      bool ok[4];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      if (inj_masks) {
-        keep[k] = 0;
-        for (int e = 0; e < nvalid; ++e)
-          keep[k] |= (inj_masks[(static_cast<size_t>(k) * B + b) * L + f0 + e] ? 1u : 0u) << e;
+      for (int e = 0; e < 4; ++e) ok[e] = (i0 + e >= 0) && (i0 + e < total);
+      if (full) {
+        const float4 v = *reinterpret_cast<const float4*>(mu + i0);
+        m[0] = v.x; m[1] = v.y; m[2] = v.z; m[3] = v.w;
       } else {
-        const uint32_t bits = philox_mask16(seed, STREAM_TRAIN_MASK, static_cast<unsigned long long>(row_offset + b),
-                                            static_cast<uint32_t>(k), static_cast<uint32_t>(f0 >> 4));
-        keep[k] = (bits >> (f0 & 15)) & 0xFu;
-      }
-    }
-    float xp[4], xc[4], xs[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float xt = sa * m[e] + om * nz[e];
-      const float xq = m[e] + mu_coef * nz[e];
-      xp[e] = ((keep[0] >> e) & 1u) ? 2.0f * xt : 0.0f;
-      xc[e] = ((keep[1] >> e) & 1u) ? 2.0f * m[e] : 0.0f;
-      xs[e] = ((keep[2] >> e) & 1u) ? 2.0f * xq : 0.0f;
-    }
-    if (vec) {
-      if (noise_out) *reinterpret_cast<float4*>(noise_out + off) = make_float4(nz[0], nz[1], nz[2], nz[3]);
-      *reinterpret_cast<float4*>(in_pert + off) = make_float4(xp[0], xp[1], xp[2], xp[3]);
-      *reinterpret_cast<float4*>(in_clean + off) = make_float4(xc[0], xc[1], xc[2], xc[3]);
-      *reinterpret_cast<float4*>(in_shift + off) = make_float4(xs[0], xs[1], xs[2], xs[3]);
-    } else {
-      for (int e = 0; e < nvalid; ++e) {
-        if (noise_out) noise_out[off + e] = nz[e];
-        in_pert[off + e] = xp[e];
-        in_clean[off + e] = xc[e];
-        in_shift[off + e] = xs[e];
+        for (int e = 0; e < 4; ++e) if (ok[e]) m[e] = mu[i0 + e];
       }
-    }
-    if (masks_out) {
-      for (int k = 0; k < 3; ++k)
-        for (int e = 0; e < nvalid; ++e)
-          masks_out[(static_cast<size_t>(k) * B + b) * L + f0 + e] = static_cast<uint8_t>((keep[k] >> e) & 1u);
+      if (inj_noise) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (ok[e]) nz[e] = inj_noise[i0 + e];
+      } else {
+        const u32x4 r4 = philox4x32_10_keys(static_cast<uint32_t>(gq), static_cast<uint32_t>(gq >> 32), 0u, STREAM_TRAIN_NOISE, K);
+        box_muller_fast(r4.x, r4.y, nz[0], nz[1]);
+        box_muller_fast(r4.z, r4.w, nz[2], nz[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) nz[e] *= nd;
+      }
+      // rows of the four elements (a quad straddles two rows when L % 4 != 0)
+      const long long ic = i0 < 0 ? 0 : i0;
+      const long long b0 = ic / L;
+      const int f_first = static_cast<int>(ic - b0 * L);
+      float xp[4], xc[4], xs[4];
+      uint32_t kb[3] = {0u, 0u, 0u};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!ok[e]) { xp[e] = xc[e] = xs[e] = 0.f; continue; }
+        const long long ie = i0 + e;
+        const long long be = (L >= 4) ? b0 + ((f_first + static_cast<int>(ie - ic)) >= L ? 1 : 0) : ie / L;
+        const float abt = __ldg(ab + __ldg(t + be));
+        const float sa = sqrtf(abt), om = 1.0f - abt;
+        const int bit = 4 * j + e;
+        if (inj_masks) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) kb[k] |= (inj_masks[static_cast<size_t>(k) * total + ie] ? 1u : 0u) << e;
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) kb[k] |= ((keep[k] >> bit) & 1u) << e;
+        }
+        const float xt = sa * m[e] + om * nz[e];
+        const float xq = m[e] + mu_coef * nz[e];
+        xp[e] = ((kb[0] >> e) & 1u) ? 2.0f * xt : 0.0f;
+        xc[e] = ((kb[1] >> e) & 1u) ? 2.0f * m[e] : 0.0f;
+        xs[e] = ((kb[2] >> e) & 1u) ? 2.0f * xq : 0.0f;
+      }
+      if (full) {
+        if (noise_out) __stcs(reinterpret_cast<float4*>(noise_out + i0), make_float4(nz[0], nz[1], nz[2], nz[3]));
+        __stcs(reinterpret_cast<float4*>(in_pert + i0), make_float4(xp[0], xp[1], xp[2], xp[3]));
+        __stcs(reinterpret_cast<float4*>(in_clean + i0), make_float4(xc[0], xc[1], xc[2], xc[3]));
+        __stcs(reinterpret_cast<float4*>(in_shift + i0), make_float4(xs[0], xs[1], xs[2], xs[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (!ok[e]) continue;
+          if (noise_out) noise_out[i0 + e] = nz[e];
+          in_pert[i0 + e] = xp[e];
+          in_clean[i0 + e] = xc[e];
+          in_shift[i0 + e] = xs[e];
+        }
+      }
+      if (masks_out) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (ok[e])
+            for (int k = 0; k < 3; ++k) masks_out[static_cast<size_t>(k) * total + i0 + e] = static_cast<uint8_t>((kb[k] >> e) & 1u);
+      }
     }
   }
 }
@@ -323,7 +356,7 @@ int sdrm_noise_inputs(const float* d_mu, const int64_t* d_t, const float* d_ab, 
   if (!d_mu || !d_t || !d_ab || !d_in_pert || !d_in_clean || !d_in_shift)
     return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_noise_inputs: null pointer");
   if (B <= 0 || L <= 0) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_noise_inputs: bad shape");
-  const long long total = B * ((L + 3) / 4);
+  const long long total = (B * L + 15) / 16;   // one thread per 16 elements (a warp per 512)
   noise_inputs_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_mu, reinterpret_cast<const long long*>(d_t), d_ab, B, L, noise_divider, static_cast<float>(mu_coef), seed, row_offset, d_inj_noise,
       d_inj_masks, d_noise_out, d_in_pert, d_in_clean, d_in_shift, d_masks_out);

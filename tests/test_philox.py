@@ -21,9 +21,13 @@ def test_normals_and_masks_statistics():
     z = ph.normals(12345, ph.STREAM_NORMAL, np.arange(2000), 3, 256).astype(np.float64)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
     assert np.isfinite(z).all()
-    m = ph.keep_masks(12345, ph.STREAM_MASK, np.arange(2000), 3, 250)
-    assert m.shape == (2000, 250) and set(np.unique(m)) == {0, 1}
-    assert abs(m.mean() - 0.5) < 0.005
+    m = ph.train_keep_masks(12345, 0, 2000, 250)
+    assert m.shape == (3, 2000, 250) and set(np.unique(m)) == {0, 1}
+    assert abs(m.mean() - 0.5) < 0.005 and not np.array_equal(m[0], m[1])
+    zt = ph.train_normals(12345, 7, 500, 150).astype(np.float64)
+    assert abs(zt.mean()) < 0.02 and abs(zt.std() - 1.0) < 0.02
+    assert np.array_equal(ph.train_normals(12345, 107, 400, 150), ph.train_normals(12345, 7, 500, 150)[100:])
+    assert np.array_equal(ph.train_keep_masks(12345, 107, 400, 150), ph.train_keep_masks(12345, 7, 500, 150)[:, 100:])
     m = ph.keep_masks128(12345, ph.STREAM_MASK, np.arange(2000), 3, 250)
     assert m.shape == (2000, 250) and set(np.unique(m)) == {0, 1}
     assert abs(m.mean() - 0.5) < 0.005

@@ -35,16 +35,17 @@ def test_training_step_matches_reference_golden(name):
 def test_noise_inputs_philox_stream_matches_restatement():
     from sdrm_b200.training import CudaLossBackend
     be = CudaLossBackend()
-    B, L, T, nd, seed, off = 300, 150, 43, 0.2, 987654321, 5000
+    B, L, T, nd, seed, off = 300, 150, 43, 0.2, 987654321, 5001     # 5001 * 150 is not a multiple of 512: ragged first block
     mu = torch.randn(B, L, device="cuda")
     t = torch.randint(1, T + 1, (B,), device="cuda")
     _, _, ab_t = orc.make_schedule(T)
     noise, in_pert, in_clean, in_shift, masks = be.noise_inputs(mu, t, ab_t.cuda(), nd, 0.1, seed, off, want_masks=True)
-    rows = np.arange(off, off + B)
-    z = philox_ref.normals(seed, philox_ref.STREAM_TRAIN_NOISE, rows, 0, L) * np.float32(nd)
+    z = philox_ref.train_normals(seed, off, B, L) * np.float32(nd)
     assert np.allclose(noise.cpu().numpy(), z, rtol=2e-5, atol=2e-6)
-    for k in range(3):
-        assert np.array_equal(masks[k].cpu().numpy(), philox_ref.keep_masks(seed, philox_ref.STREAM_TRAIN_MASK, rows, k, L))
+    assert np.array_equal(masks.cpu().numpy(), philox_ref.train_keep_masks(seed, off, B, L))
+    # row sharding does not change the streams: rows [100, 300) generated on their own equal the slice of the whole
+    part = be.noise_inputs(mu[100:].contiguous(), t[100:].contiguous(), ab_t.cuda(), nd, 0.1, seed, off + 100, want_masks=True)
+    assert torch.equal(part[0], noise[100:]) and torch.equal(part[4], masks[:, 100:])
     x_t = orc.perturb_input(mu.cpu(), t.cpu(), noise.cpu(), ab_t)
     keep = masks.cpu().float()
     assert torch.allclose(in_pert.cpu(), x_t * keep[0] * 2, atol=1e-6)

@@ -132,19 +132,36 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // stats += {sum r, sum r^2, sum (sd-r)^2, sum (r-sx)^2, count};  r = pred - mu, sd = (psx - sx)/mu_coef^2
+// float4 loads (the four arrays are flat and 16-byte aligned in every caller; otherwise the scalar loop takes all of it);
+// the four terms of a quad are summed in fp32 and promoted to fp64 once per quad: B200 runs FP64 at a fraction of the fp32
+// rate, and one DADD per element and statistic made this kernel ALU-bound.
 __global__ void __launch_bounds__(256) loss_stats_kernel(const float* __restrict__ pred, const float* __restrict__ sx,
                                                          const float* __restrict__ psx, const float* __restrict__ mu,
                                                          long long count, float mu2, double* __restrict__ stats) {
   double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float r = pred[i] - mu[i];
-    const float sd = (psx[i] - sx[i]) / mu2;
-    const float d1 = sd - r, d2 = r - sx[i];
-    s0 += r;
-    s1 += static_cast<double>(r) * r;
-    s2 += static_cast<double>(d1) * d1;
-    s3 += static_cast<double>(d2) * d2;
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = (((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(sx) | reinterpret_cast<uintptr_t>(psx) |
+                      reinterpret_cast<uintptr_t>(mu)) & 15) == 0);
+  const long long n4 = vec ? (count >> 2) : 0;
+  auto term = [&](float p, float s, float q, float m, float& a0, float& a1, float& a2, float& a3) {
+    const float r = p - m;
+    const float sd = (q - s) / mu2;
+    const float d1 = sd - r, d2 = r - s;
+    a0 += r; a1 = fmaf(r, r, a1); a2 = fmaf(d1, d1, a2); a3 = fmaf(d2, d2, a3);
+  };
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 p = __ldcs(reinterpret_cast<const float4*>(pred) + i), s = __ldcs(reinterpret_cast<const float4*>(sx) + i);
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(psx) + i), m = __ldcs(reinterpret_cast<const float4*>(mu) + i);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    term(p.x, s.x, q.x, m.x, a0, a1, a2, a3); term(p.y, s.y, q.y, m.y, a0, a1, a2, a3);
+    term(p.z, s.z, q.z, m.z, a0, a1, a2, a3); term(p.w, s.w, q.w, m.w, a0, a1, a2, a3);
+    s0 += a0; s1 += a1; s2 += a2; s3 += a3;
+  }
+  for (long long i = (n4 << 2) + tid; i < count; i += nth) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    term(pred[i], sx[i], psx[i], mu[i], a0, a1, a2, a3);
+    s0 += a0; s1 += a1; s2 += a2; s3 += a3;
   }
   __shared__ double sh[4][8];
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
@@ -175,15 +192,38 @@ __global__ void __launch_bounds__(256) loss_seeds_kernel(const float* __restrict
   const float two_c_over_N = static_cast<float>(2.0 * c / N);
   const float kv = static_cast<float>(kvar), mr = static_cast<float>(mean_r);
   if (blockIdx.x == 0 && threadIdx.x == 0 && loss_out) loss_out[0] = static_cast<float>(0.5 * (A + Bm) / den);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < count;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float r = pred[i] - mu[i];
-    const float sd = (psx[i] - sx[i]) / mu2;
-    const float d1 = sd - r, d2 = r - sx[i];
+  auto seed = [&](float p, float s, float q, float m, float& gp, float& gs, float& gq) {
+    const float r = p - m;
+    const float sd = (q - s) / mu2;
+    const float d1 = sd - r, d2 = r - s;
     const float gsd = two_c_over_N * d1;
-    if (g_psx) g_psx[i] = gsd / mu2;
-    if (g_sx) g_sx[i] = -two_c_over_N * d2 - gsd / mu2;
-    if (g_pred) g_pred[i] = two_c_over_N * (d2 - d1) + kv * (r - mr);
+    gq = gsd / mu2;
+    gs = -two_c_over_N * d2 - gsd / mu2;
+    gp = two_c_over_N * (d2 - d1) + kv * (r - mr);
+  };
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  const bool vec = g_pred && g_sx && g_psx &&
+                   (((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(sx) | reinterpret_cast<uintptr_t>(psx) |
+                      reinterpret_cast<uintptr_t>(mu) | reinterpret_cast<uintptr_t>(g_pred) | reinterpret_cast<uintptr_t>(g_sx) |
+                      reinterpret_cast<uintptr_t>(g_psx)) & 15) == 0);
+  const long long n4 = vec ? (count >> 2) : 0;
+  for (long long i = tid; i < n4; i += nth) {
+    const float4 p = __ldcs(reinterpret_cast<const float4*>(pred) + i), s = __ldcs(reinterpret_cast<const float4*>(sx) + i);
+    const float4 q = __ldcs(reinterpret_cast<const float4*>(psx) + i), m = __ldcs(reinterpret_cast<const float4*>(mu) + i);
+    float4 gp, gs, gq;
+    seed(p.x, s.x, q.x, m.x, gp.x, gs.x, gq.x); seed(p.y, s.y, q.y, m.y, gp.y, gs.y, gq.y);
+    seed(p.z, s.z, q.z, m.z, gp.z, gs.z, gq.z); seed(p.w, s.w, q.w, m.w, gp.w, gs.w, gq.w);
+    __stcs(reinterpret_cast<float4*>(g_pred) + i, gp);
+    __stcs(reinterpret_cast<float4*>(g_sx) + i, gs);
+    __stcs(reinterpret_cast<float4*>(g_psx) + i, gq);
+  }
+  for (long long i = (n4 << 2) + tid; i < count; i += nth) {
+    float gp, gs, gq;
+    seed(pred[i], sx[i], psx[i], mu[i], gp, gs, gq);
+    if (g_psx) g_psx[i] = gq;
+    if (g_sx) g_sx[i] = gs;
+    if (g_pred) g_pred[i] = gp;
   }
 }
 

@@ -1,2 +1,2 @@
 timeout 900 python -m pytest tests/test_training_gpu.py -x -q 2>&1 | tail -3
-python tools/bench_train_kernels.py 2>&1 | grep "K2 noise"
+python tools/bench_train_kernels.py 2>&1 | grep "K2"

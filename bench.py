@@ -178,6 +178,7 @@ def run_ours(args, w, rank, world, local_rank):
 
     from sdrm_b200 import _lib as _l
     _l.load().sdrm_set_cluster_override(args.cluster)
+    _l.load().sdrm_set_subtile_override(args.subtiles)
     _l.load().sdrm_debug_set_flags(int(os.environ.get("SDRM_DEBUG_FLAGS", "0")))
     for i in range(args.warmup):
         step(1000 + i)
@@ -300,7 +301,7 @@ def run_ours(args, w, rank, world, local_rank):
                        **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
                        "l2": "each step writes n*I*4 bytes of logits (>> 126 MB L2 for cfg5); no reuse across steps",
                        "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
-            "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "gpu_launches": launches_per_step * args.steps,
+            "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "subtiles": args.subtiles, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         emit(line)
@@ -338,6 +339,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cluster", type=int, default=0, help="force the weight-multicast cluster size (1, 2, 4); 0 = auto")
+    ap.add_argument("--subtiles", type=int, default=0, help="row tiles a CTA pair interleaves (1, 2); 0 = auto")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))

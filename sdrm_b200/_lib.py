@@ -27,6 +27,8 @@ SIGNATURES = {
     "sdrm_probe_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "sdrm_probe_set_repeat": (None, [C.c_int]),
     "sdrm_set_cluster_override": (None, [C.c_int]),
+    "sdrm_set_subtile_override": (None, [C.c_int]),
+    "sdrm_debug_set_grid_limit": (None, [C.c_int]),
     "sdrm_debug_set_trace": (None, [_P]),
     "sdrm_debug_set_flags": (None, [C.c_int]),
     "sdrm_last_cluster_size": (C.c_int, [_P]),

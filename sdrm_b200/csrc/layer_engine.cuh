@@ -19,6 +19,7 @@ constexpr int NUM_STAGES = 4;
 constexpr int MAX_STEP_LAYERS = 8;                 // 2 + nh, nh <= 6
 constexpr int NUM_ACT_BUFS = 4;
 constexpr int MAX_ACT_CHUNKS = 8;                  // N chunks of an activation-producing layer (features <= 8 * MAX_NC)
+constexpr int MAX_SUB = 2;                         // row tiles a CTA interleaves layer by layer (ChainParams::n_sub)
 constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter
 constexpr int EPI_SUB = EPI_WARPS / 4;             // warps sharing a lane quarter split the column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
@@ -64,6 +65,7 @@ struct ChainParams {
   int n_step, n_dec;
   int T, L, Lg16;         // Lg16 = ceil(L / 16) column groups of the fp32 state
   int preloaded_input;    // probe mode: activation images were packed per TILE by the host
+  int n_sub;              // 1 or 2: row tiles per CTA iteration, interleaved layer by layer (scratch slot = CTA * n_sub + s)
   long long n_rows, row_offset;
   const float* coef;      // [T+1][4] = c1, c2, sigma*nd, 0   (denoise_add_noise, train_SDRM.py:20-25)
   const int32_t* t_start; // per-row start step or nullptr (indexed by physical row)

@@ -35,6 +35,24 @@
 #ifndef SDRM_NSTG_PAIR
 #define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 (with 31 KB stages, MAX_NC = 240) measured no faster
 #endif
+#ifndef SDRM_DISCARD_DEAD
+#define SDRM_DISCARD_DEAD 0   // (measured slower, 312.9 vs 308.2 ms per cfg-5 shard: off) drop a chain layer's input images from L2 once its last UMMA has read them (no write-back of dead lines)
+#endif
+#ifndef SDRM_PREFETCH_STATE
+#define SDRM_PREFETCH_STATE 0 // L2 prefetch of the fp32 state columns one chunk ahead of the posterior epilogue (measured slower,
+                              // 302.9 vs 295.6 ms per cfg-5 shard: the earlier fills evict live activation lines; off)
+#endif
+#ifndef SDRM_DEFER_ALL
+#define SDRM_DEFER_ALL 1      // interleaved sub-tiles: every chunk is published one chunk late (no fence right behind its stores)
+#endif
+#ifndef SDRM_STATE_CS
+#define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
+#endif
+#if SDRM_STATE_CS
+#define SDRM_ST_HINT ".cs"
+#else
+#define SDRM_ST_HINT ""
+#endif
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
 #define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
@@ -59,7 +77,7 @@ __device__ __forceinline__ float* xstate_ptr8(float* xs, int g16, int half, int 
 __device__ __forceinline__ void xs_load16(float* xs, int g16, int r, float (&x)[16]) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf)
-    asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    asm volatile("ld.global" SDRM_ST_HINT ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(x[8 * hf + 0]), "=f"(x[8 * hf + 1]), "=f"(x[8 * hf + 2]), "=f"(x[8 * hf + 3]), "=f"(x[8 * hf + 4]),
                    "=f"(x[8 * hf + 5]), "=f"(x[8 * hf + 6]), "=f"(x[8 * hf + 7])
                  : "l"(xstate_ptr8(xs, g16, hf, r))
@@ -68,7 +86,7 @@ __device__ __forceinline__ void xs_load16(float* xs, int g16, int r, float (&x)[
 __device__ __forceinline__ void xs_store16(float* xs, int g16, int r, const float (&x)[16]) {
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf)
-    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+    asm volatile("st.global" SDRM_ST_HINT ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"l"(xstate_ptr8(xs, g16, hf, r)), "f"(x[8 * hf + 0]), "f"(x[8 * hf + 1]), "f"(x[8 * hf + 2]), "f"(x[8 * hf + 3]),
                    "f"(x[8 * hf + 4]), "f"(x[8 * hf + 5]), "f"(x[8 * hf + 6]), "f"(x[8 * hf + 7])
                  : "memory");
@@ -96,7 +114,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = CS;
   constexpr uint32_t BIAS_SLICE_BYTES = 4 * 16 * 4;   // per epilogue warp: the bias of its (at most 4) column groups of one chunk
-  static_assert(NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 256 + EPI_WARPS * BIAS_SLICE_BYTES + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 2);   // mbarriers of a CTA (map below)
+  static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * BIAS_SLICE_BYTES + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -104,7 +123,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   uint8_t* smem = smem_raw + (base_addr - raw_addr);
   const uint32_t bar_base = base_addr + NSTG * STG_BYTES;
   // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | (unused NSTG) | acc_full[2] | acc_empty[2] | tile_ready |
-  //                             act_chunk[MAX_ACT_CHUNKS]
+  //                             act_chunk[MAX_SUB][MAX_ACT_CHUNKS] | state_ready[MAX_SUB] | noise_ready[MAX_SUB]
   auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
   auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
   auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -114,14 +133,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 4);
   // one barrier per chunk INDEX: chunk c of layer l+1 cannot finish before the A producer consumed chunk c of layer l,
   // so a waiter never lags more than one phase (a single barrier would be lapped by fast chunk epilogues)
-  auto bar_act_chunk = [&](uint32_t c) { return bar_base + 8u * (3 * NSTG + 5 + c); };
-  const uint32_t bar_state_ready = bar_base + 8u * (3 * NSTG + 5 + MAX_ACT_CHUNKS);      // epilogue -> noise warps
-  const uint32_t bar_noise_ready = bar_base + 8u * (3 * NSTG + 6 + MAX_ACT_CHUNKS);      // noise warps -> epilogue
-  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS);
+  // (one set per interleaved row tile s, see "sub-tiles" below)
+  auto bar_act_chunk = [&](uint32_t s, uint32_t c) { return bar_base + 8u * (3 * NSTG + 5 + s * MAX_ACT_CHUNKS + c); };
+  auto bar_state_ready = [&](uint32_t s) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + s); };            // epilogue -> noise warps
+  auto bar_noise_ready = [&](uint32_t s) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + MAX_SUB + s); };  // noise warps -> epilogue
+  uint8_t* misc = smem + NSTG * STG_BYTES + 8 * NBAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
-  uint8_t* bias_slices = smem + ((NSTG * STG_BYTES + 8 * (3 * NSTG + 7 + MAX_ACT_CHUNKS) + 16 + 8 * EPI_WARPS + 15) & ~15);   // EPI_WARPS x BIAS_SLICE_BYTES, 16-byte aligned
+  uint8_t* bias_slices = smem + ((NSTG * STG_BYTES + 8 * NBAR + 16 + 8 * EPI_WARPS + 15) & ~15);   // EPI_WARPS x BIAS_SLICE_BYTES, 16-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,9 +158,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_acc_full(1), 1);
     mbar_init(bar_acc_empty(0), EPI_WARPS * (PAIR ? 2 : 1));   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
     mbar_init(bar_acc_empty(1), EPI_WARPS * (PAIR ? 2 : 1));
-    for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(c), EPI_WARPS);
-    mbar_init(bar_state_ready, EPI_WARPS);
-    mbar_init(bar_noise_ready, NOISE_WARPS);
+    for (int s = 0; s < MAX_SUB; ++s) {
+      for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), EPI_WARPS);
+      mbar_init(bar_state_ready(s), EPI_WARPS);
+      mbar_init(bar_noise_ready(s), NOISE_WARPS);
+    }
     mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
   }
@@ -158,8 +180,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const long long n_clusters = gridDim.x / NCTA;
   const long long my_cluster = blockIdx.x / NCTA;
   // both CTAs of a pair run the same number of tile iterations (a ghost tile past n_tiles has no valid row)
-  const int n_iters = static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);
-  auto tile_of = [&](int it) -> long long { return (static_cast<long long>(it) * n_clusters + my_cluster) * NCTA + cta_rank; };
+  const int n_local = static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);   // row tiles of this CTA
+  // Sub-tiles: an iteration works on NSUB = P.n_sub (1 or 2) row tiles at once and INTERLEAVES them layer by layer
+  // (step i: layer 0 of tile 0, layer 0 of tile 1, layer 1 of tile 0, ...).  A layer's first chunk needs the last chunk
+  // of the previous layer of the SAME tile out of its epilogue (stores + proxy fence + TMA round trip: the tensor pipe
+  // idled ~3 us of every 21 us layer, 8 us at a step boundary, and through the slow posterior epilogue); with a second,
+  // independent tile in between that dependency is a whole layer old when it is needed.  Each sub-tile has its own
+  // scratch slot (activation buffers, fp32 state, keep bits) and its own chunk / state / noise barriers; the UMMA
+  // issuer and the accumulator hand-off just see a longer chunk sequence.  An odd last tile runs alone (nsub = 1).
+  const int NSUB = P.n_sub;
+  const int n_iters = (n_local + NSUB - 1) / NSUB;
+  auto nsub_of = [&](int it) -> int { return min(NSUB, n_local - it * NSUB); };
+  auto tile_of = [&](int it, int s) -> long long {
+    return (static_cast<long long>(it * NSUB + s) * n_clusters + my_cluster) * NCTA + cta_rank;
+  };
   int* err = P.err_word;
 #ifdef SDRM_TRACE
   int trace_n = 0;
@@ -172,8 +206,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   };
 #endif
 
-  auto scratch_of = [&](long long tile) -> uint8_t* {
-    const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x);
+  auto scratch_of = [&](long long tile, int s) -> uint8_t* {
+    const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x) * NSUB + s;
     return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
   };
 
@@ -187,24 +221,26 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // ~0.5 us per k-block.  The weight stream does not depend on the previous layer's epilogue and runs ahead.
     const bool is_w = (warp == W_WARP);
     const uint64_t pol_keep = l2_policy_evict_last();
-    uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier
+    uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier (sub-tile s: bits 8s..8s+7)
+    static_assert(MAX_SUB * MAX_ACT_CHUNKS <= 32, "act_par bits");
     for (int it = 0; it < n_iters; ++it) {
-      const long long tile = tile_of(it);
-      if (!PAIR && tile >= n_tiles) break;
+      const int ns = nsub_of(it);
+      if (!PAIR && tile_of(it, 0) >= n_tiles) break;
       int T_tile = P.T;
       if (!is_w || !PAIR) {   // (single mode: T_tile may be per tile)
         mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
         T_tile = tile_T[it & 1];
       }
-      const uint8_t* sc = scratch_of(tile);
-      const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
       // Readiness of a layer's input is tracked per CHUNK of the producing layer (one barrier per chunk index): k-block
       // kb only needs the chunks covering features < 64 (kb + 1), so a layer starts while the previous layer's last
       // chunk is still in its epilogue.
       int prev_nch = 0, prev_nc = 1;
-      auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf) {
-        const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes, kind = ldref.kind;
+      auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf, int s) {
+        const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes;
         const uint8_t* w_img = ldref.w_img;
+        const uint8_t* sc = scratch_of(tile_of(it, s), s);
+        const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
+        const uint32_t par_shift = static_cast<uint32_t>(s) * MAX_ACT_CHUNKS;
         int ready = 0;
         if (!is_w) SDRM_TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
@@ -224,8 +260,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
                 if (need > prev_nch || kb == KB - 1) need = prev_nch;
                 while (ready < need) {
-                  mbar_wait(bar_act_chunk(ready), (act_par >> ready) & 1u, err, WD_PRODUCER_ACT);
-                  act_par ^= (1u << ready);
+                  mbar_wait(bar_act_chunk(s, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
+                  act_par ^= (1u << (par_shift + ready));
                   ++ready;
                 }
                 if (kb == 0) SDRM_TR(0, 2);
@@ -271,15 +307,25 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           if (!is_w) SDRM_TR(0, 3);
         }
-        prev_nch = (kind == EPI_LINEAR_OUT) ? 0 : NCH;
-        prev_nc = NC;
+      };
+      // the layer whose output the NEXT layer of the same tile reads (all sub-tiles go through the same layer sequence)
+      auto done = [&](const LayerDesc& ldref) {
+        prev_nch = (ldref.kind == EPI_LINEAR_OUT) ? 0 : ldref.NCH;
+        prev_nc = ldref.NC;
       };
       // chain layers ping-pong between activation buffers 0 and 1 (in = parity of the layer count so far); only two
-      // hot buffers per CTA keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
+      // hot buffers per tile keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
-        for (int l = 0; l < P.n_step; ++l) { run(P.step[l], &P.tm_step_w[l], cur, cur); cur ^= 1; }
-      for (int l = 0; l < P.n_dec; ++l) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo);
+        for (int l = 0; l < P.n_step; ++l) {
+          for (int s = 0; s < ns; ++s) run(P.step[l], &P.tm_step_w[l], cur, cur, s);
+          done(P.step[l]);
+          cur ^= 1;
+        }
+      for (int l = 0; l < P.n_dec; ++l) {
+        for (int s = 0; s < ns; ++s) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo, s);
+        done(P.dec[l]);
+      }
     }
   } else if (warp == M_WARP) {
     setmaxnreg_dec<REGS_CTRL>();
@@ -290,7 +336,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       // whole warp converged, one elected lane issues (see the producer comment)
       uint32_t stage = 0, sphase = 0, cc = 0;
       for (int it = 0; it < n_iters; ++it) {
-        if (!PAIR && tile_of(it) >= n_tiles) break;
+        if (!PAIR && tile_of(it, 0) >= n_tiles) break;
+        const int ns = nsub_of(it);
         int T_tile = P.T;   // the pair mode only runs full-resolution chains (same T for both row tiles)
         if (!PAIR) {
           mbar_wait(bar_tile_ready, it & 1, err, WD_MMA_TILE);
@@ -348,8 +395,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
         };
         for (int i = T_tile; i >= 1; --i)
-          for (int l = 0; l < P.n_step; ++l) run(P.step[l]);
-        for (int l = 0; l < P.n_dec; ++l) run(P.dec[l]);
+          for (int l = 0; l < P.n_step; ++l)
+            for (int s = 0; s < ns; ++s) run(P.step[l]);
+        for (int l = 0; l < P.n_dec; ++l)
+          for (int s = 0; s < ns; ++s) run(P.dec[l]);
       }
     }
   } else if (warp > A_WARP) {
@@ -400,27 +449,54 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 
     // zero the activation buffers once: K-padding columns must read as exact zeros
     if (!P.preloaded_input) {
-      uint4* z = reinterpret_cast<uint4*>(scratch_of(blockIdx.x));
-      const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
-      for (size_t i = threadIdx.x; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      for (int s = 0; s < NSUB; ++s) {
+        uint4* z = reinterpret_cast<uint4*>(scratch_of(0, s));
+        const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
+        for (size_t i = threadIdx.x; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+      }
       epi_bar_sync();
     }
-    uint32_t noise_par = 0;
+    uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
+    uint32_t pending_bar = 0; // activation-chunk barrier whose publication (proxy fence + arrive) is deferred to the next chunk
+    auto publish_pending = [&]() {
+      if (pending_bar) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane0) mbar_arrive(pending_bar);
+        pending_bar = 0;
+        SDRM_TR_EPI(5);
+      }
+    };
+    // context of the sub-tile a layer works on (set_ctx): scratch pointers are recomputed, the row facts are kept per sub-tile
+    uint8_t* sc = nullptr;
+    float* xs = nullptr;
+    const uint16_t* mask_row = nullptr;
+    bool valid = false, valid0 = false, valid1 = false;
+    long long row = 0, row0 = 0, row1 = 0;
+    int t_row = 0, t_row0 = 0, t_row1 = 0;
     for (; it < n_iters; ++it) {
-      const long long tile = tile_of(it);
-      if (!PAIR && tile >= n_tiles) break;
-      uint8_t* sc = scratch_of(tile);
-      float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
-      const uint16_t* mask_row = reinterpret_cast<const uint16_t*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
-      const long long prow = tile * TILE_M + r;   // physical row of this launch
-      const bool valid = prow < P.n_rows;
-      const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
-      const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
-      int t_row = P.T;
-      if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
+      if (!PAIR && tile_of(it, 0) >= n_tiles) break;
+      const int ns = nsub_of(it);
+      auto set_ctx = [&](int s) {
+        sc = scratch_of(tile_of(it, s), s);
+        xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+        mask_row = reinterpret_cast<const uint16_t*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
+        valid = s ? valid1 : valid0;
+        row = s ? row1 : row0;
+        t_row = s ? t_row1 : t_row0;
+      };
 
-      // ---- tile start step = max over rows
-      int m = t_row;
+      // ---- row facts of every sub-tile; tile start step = max over rows (and sub-tiles)
+      int m = 0;
+      for (int s = 0; s < ns; ++s) {
+        const long long prow = tile_of(it, s) * TILE_M + r;   // physical row of this launch
+        const bool v = prow < P.n_rows;
+        const long long lrow = (v && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
+        int tr = P.T;
+        if (P.t_start) tr = v ? P.t_start[prow] : 0;
+        if (s == 0) { valid0 = v; row0 = lrow; t_row0 = tr; } else { valid1 = v; row1 = lrow; t_row1 = tr; }
+        m = max(m, tr);
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
       if (lane == 0) warp_max[(it & 1) * EPI_WARPS + warp] = m;
@@ -433,47 +509,51 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38).  Once per tile: not performance critical.
       if (P.n_step > 0) {
         const PhiloxKeys K = philox_make_keys(P.seed);
-        uint8_t* in0_row = sc + row_off;   // the first chain layer reads activation buffer 0
-        for (int g = sub; g < P.Lg16; g += EPI_SUB) {
-          float x[16];
+        for (int s = 0; s < ns; ++s) {
+          set_ctx(s);
+          const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
+          uint8_t* in0_row = sc + row_off;   // the first chain layer reads activation buffer 0
+          for (int g = sub; g < P.Lg16; g += EPI_SUB) {
+            float x[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float z4[4];
-            if (P.inj_xT) {
+            for (int j = 0; j < 4; ++j) {
+              float z4[4];
+              if (P.inj_xT) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int f = g * 16 + j * 4 + e;
+                  z4[e] = (valid && f < P.L) ? P.inj_xT[static_cast<size_t>(row) * P.L + f] : 0.0f;
+                }
+              } else {
+                philox_normal4_keys(K, STREAM_NORMAL, grow, 0u, static_cast<uint32_t>(g * 4 + j), z4);
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int f = g * 16 + j * 4 + e;
-                z4[e] = (valid && f < P.L) ? P.inj_xT[static_cast<size_t>(row) * P.L + f] : 0.0f;
+                x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;   // padding columns / rows stay exactly 0 for the whole chain
               }
-            } else {
-              philox_normal4_keys(K, STREAM_NORMAL, grow, 0u, static_cast<uint32_t>(g * 4 + j), z4);
             }
+            xs_store16(xs, g, r, x);
+            // keep mask of the first step (the noise warps produce the masks of all later steps)
+            uint32_t keep = 0;
+            if (valid) {
+              if (P.inj_mask) {
+                const uint8_t* mp = P.inj_mask + (static_cast<size_t>(T_tile) * P.n_rows + row) * P.L;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int f = g * 16 + j * 4 + e;
-              x[j * 4 + e] = (valid && f < P.L) ? z4[e] : 0.0f;   // padding columns / rows stay exactly 0 for the whole chain
-            }
-          }
-          xs_store16(xs, g, r, x);
-          // keep mask of the first step (the noise warps produce the masks of all later steps)
-          uint32_t keep = 0;
-          if (valid) {
-            if (P.inj_mask) {
-              const uint8_t* mp = P.inj_mask + (static_cast<size_t>(T_tile) * P.n_rows + row) * P.L;
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int f = g * 16 + e;
-                if (f < P.L && mp[f]) keep |= (1u << e);
+                for (int e = 0; e < 16; ++e) {
+                  const int f = g * 16 + e;
+                  if (f < P.L && mp[f]) keep |= (1u << e);
+                }
+              } else {
+                const u32x4 w4 = philox_mask128(K, STREAM_MASK, grow, static_cast<uint32_t>(T_tile), static_cast<uint32_t>(g >> 3));
+                const uint32_t wsel = ((g >> 1) & 3) == 0 ? w4.x : ((g >> 1) & 3) == 1 ? w4.y : ((g >> 1) & 3) == 2 ? w4.z : w4.w;
+                keep = (wsel >> (16 * (g & 1))) & 0xFFFFu;
               }
-            } else {
-              const u32x4 w4 = philox_mask128(K, STREAM_MASK, grow, static_cast<uint32_t>(T_tile), static_cast<uint32_t>(g >> 3));
-              const uint32_t wsel = ((g >> 1) & 3) == 0 ? w4.x : ((g >> 1) & 3) == 1 ? w4.y : ((g >> 1) & 3) == 2 ? w4.z : w4.w;
-              keep = (wsel >> (16 * (g & 1))) & 0xFFFFu;
             }
+            uint32_t pk[8];
+            dropout_pack(x, keep, pk);
+            store_act(in0_row, g * 16, pk);
           }
-          uint32_t pk[8];
-          dropout_pack(x, keep, pk);
-          store_act(in0_row, g * 16, pk);
         }
       }
       if (warp == 0 && lane == 0) tile_T[it & 1] = T_tile;
@@ -482,7 +562,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       if (lane == 0) mbar_arrive(bar_tile_ready);
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
-      auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
+      auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s, int dead_buf, bool pf_next) {
         constexpr int KIND = decltype(kind_c)::value;
         uint8_t* out_hi_row = sc + static_cast<size_t>(out_hi_buf) * P.act_buf_bytes + row_off;
         uint8_t* out_lo_row = sc + static_cast<size_t>(out_lo_buf) * P.act_buf_bytes + row_off;
@@ -498,12 +578,31 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           const float4 cf = __ldg(reinterpret_cast<const float4*>(P.coef) + step);
           c12 = (valid && step <= t_row) ? cf.x * cf.y : 0.0f;   // rows not started yet (multi-resolution) keep their state
           // the noise warps have turned the state into x_i / sqrt(a_i) + sqrt(b_i) nd z_i and written the keep masks of step i-1
-          mbar_wait_sleepy(bar_noise_ready, noise_par, err, WD_EPI_NOISE, 128);
-          noise_par ^= 1;
+          mbar_wait_sleepy(bar_noise_ready(s), (noise_par >> s) & 1u, err, WD_EPI_NOISE, 128);
+          noise_par ^= 1u << s;
         }
         const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
         const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT;
+        // With a second sub-tile in flight the next layer of THIS tile is a whole layer away: every chunk is published one
+        // chunk late, so that no fence.proxy.async sits right behind its own stores (the membar inside it waits for them to
+        // reach L2: 10 % of the epilogue warps' time in the r01 profile).  A tile running alone publishes its last two
+        // chunks right away: the next layer's tail k-blocks wait for them.
+        const bool defer_all = SDRM_DEFER_ALL && ns > 1;
+        // L2 prefetch of the state columns this warp's groups of posterior chunk c touch (64 lines of 128 B: 4 groups x 2
+        // halves x 1 KB): the state streams through HBM between steps, and with only one group requested ahead every group of
+        // the posterior epilogue waited out a DRAM round trip (its chunks took 2x as long as their UMMAs).
+        auto prefetch_state = [&](int g16_base, int ng) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int li = lane + 32 * k;
+            const int g = sub + EPI_SUB * (li >> 4);
+            if (g < ng && g16_base + g < P.Lg16) {
+              const uint8_t* pl = reinterpret_cast<const uint8_t*>(xstate_ptr8(xs, g16_base + g, (li >> 3) & 1, q * 32)) + (li & 7) * 128;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
+            }
+          }
+        };
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
         // warp stages the 64 floats of its own groups of a chunk in a private shared-memory slice (lane l holds elements
         // 2l, 2l+1: group slot l / 8, columns 2 (l % 8) ..) one chunk ahead, and the group loop reads them with LDS.128.
@@ -536,22 +635,28 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // does not depend on the accumulator: ask before waiting (first chunk only: later chunks fence first, and a membar
           // would wait for these loads to return)
           if (KIND == EPI_POSTERIOR && c == 0 && sub < ngroups) request_state(sub);
+          if (SDRM_PREFETCH_STATE) {
+            if (KIND == EPI_POSTERIOR && c + 1 < NCH) prefetch_state(((c + 1) * NC) >> 4, ngroups);
+            if (KIND != EPI_POSTERIOR && pf_next && c == NCH - 1) prefetch_state(0, P.step[P.n_step - 1].NC >> 4);
+          }
           SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          if (c > 0 && c < NCH - 1 && publishes) {   // chunk c-1 <= NCH-3
-            // Deferred publication of the PREVIOUS chunk (same layer): its stores were issued a whole accumulator wait ago, so
-            // the membar inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only
-            // the next layer reads these activations and it cannot finish its first chunk before this layer's last one.
-            // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The LAST
-            // chunk's epilogue is the critical path of the layer boundary (timeline: the next layer's first chunk takes twice
-            // as long as the others), so nothing is deferred into it.
-            fence_proxy_async();
-            __syncwarp();
-            if (lane0) mbar_arrive(bar_act_chunk(c - 1));
-            SDRM_TR_EPI(5);
+          if (SDRM_DISCARD_DEAD && dead_buf >= 0 && c == NCH - 1) {
+            // The layer's last UMMA has completed, so every TMA read of its input images is done and nothing reads them
+            // again: the next layer of this tile overwrites that buffer.  Dropping the (dirty) lines from L2 now saves their
+            // write-back to HBM (1.44 MB per tile and step at cfg 5, 40 % of the kernel's DRAM traffic) and frees L2
+            // capacity for the live buffers.  Thread (row r, sub) drops the 128-byte row r of k-blocks sub, sub + 4, ...
+            uint8_t* drow = sc + static_cast<size_t>(dead_buf) * P.act_buf_bytes + row_off;
+            for (int kb = sub; kb < ld.KB; kb += EPI_SUB)
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(drow + static_cast<size_t>(kb) * A_TILE_BYTES) : "memory");
           }
+          // Deferred publication of the PREVIOUS chunk: its stores were issued a whole accumulator wait ago, so the membar
+          // inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only the next
+          // layer reads these activations and it cannot finish its first chunk before this layer's last one.
+          // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)
+          publish_pending();
           if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
           if (KIND == EPI_POSTERIOR && c > 0 && sub < ngroups) request_state(sub);
           if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
@@ -659,33 +764,35 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
           // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
-          if (publishes && c >= NCH - 2) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane0) mbar_arrive(bar_act_chunk(c));
-            SDRM_TR_EPI(5);
+          if (publishes) {
+            pending_bar = bar_act_chunk(s, c);
+            if (!defer_all && c >= NCH - 2) publish_pending();
           }
         }
         if (KIND == EPI_POSTERIOR && step > 1) {
           __syncwarp();
-          if (lane0) mbar_arrive(bar_state_ready);   // x_{i-1} is complete: the noise warps may prepare step i-1
+          if (lane0) mbar_arrive(bar_state_ready(s));   // x_{i-1} is complete: the noise warps may prepare step i-1
         }
       };
-      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf) {
+      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s, int dead_buf, bool pf_next) {
+        set_ctx(s);
         switch (ld.kind) {
-          case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
-          case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
-          case EPI_TANH_SPLIT: run(std::integral_constant<int, EPI_TANH_SPLIT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
-          default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf); break;
+          case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, pf_next); break;
+          case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
+          case EPI_TANH_SPLIT: run(std::integral_constant<int, EPI_TANH_SPLIT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
+          default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
         }
       };
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
         for (int l = 0; l < P.n_step; ++l) {
-          run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2);   // x0 lo -> buffer 2
+          for (int s = 0; s < ns; ++s)
+            run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2, s, cur, l == P.n_step - 2);   // x0 lo -> buffer 2; input = cur
           cur ^= 1;
         }
-      for (int l = 0; l < P.n_dec; ++l) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo);
+      for (int l = 0; l < P.n_dec; ++l)
+        for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s, -1, false);
+      publish_pending();
     }
   } else {
     // ======================================= noise warps ========================================
@@ -697,27 +804,29 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     setmaxnreg_dec<REGS_NOISE>();
     const int r = (warp - NOISE_WARP0) * 32 + lane;
     const PhiloxKeys K = philox_make_keys(P.seed);
-    uint32_t st_par = 0;
+    uint32_t st_par = 0;                     // bit s: parity of sub-tile s's state_ready barrier
     const int L = P.L, Lg16 = P.Lg16;
     const int full_groups = L >> 4;          // groups without padding columns
     for (int it = 0; it < n_iters; ++it) {
-      const long long tile = tile_of(it);
-      if (!PAIR && tile >= n_tiles) break;
-      uint8_t* sc = scratch_of(tile);
-      float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
-      uint4* mask_row = reinterpret_cast<uint4*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
-      const long long prow = tile * TILE_M + r;
-      const bool valid = prow < P.n_rows;
-      const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;
-      const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
-      int t_row = P.T;
-      if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
+      if (!PAIR && tile_of(it, 0) >= n_tiles) break;
+      const int ns = nsub_of(it);
       mbar_wait_sleepy(bar_tile_ready, it & 1, err, WD_NOISE_TILE, 128);   // x_T is in place
       const int T_tile = (P.n_step == 0) ? 0 : tile_T[it & 1];
-      for (int i = T_tile; i >= 1; --i) {
+      for (int i = T_tile; i >= 1; --i)
+      for (int s = 0; s < ns; ++s) {
+        const long long tile = tile_of(it, s);
+        uint8_t* sc = scratch_of(tile, s);
+        float* xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
+        uint4* mask_row = reinterpret_cast<uint4*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
+        const long long prow = tile * TILE_M + r;
+        const bool valid = prow < P.n_rows;
+        const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;
+        const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
+        int t_row = P.T;
+        if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
         if (i != T_tile) {
-          mbar_wait_sleepy(bar_state_ready, st_par, err, WD_NOISE_STATE, 128);
-          st_par ^= 1;
+          mbar_wait_sleepy(bar_state_ready(s), (st_par >> s) & 1u, err, WD_NOISE_STATE, 128);
+          st_par ^= 1u << s;
         }
         // ---- (1) keep masks of step i-1 (F.dropout p = .5 of the NEXT forward, train_SDRM.py:100)
         if (i > 1) {
@@ -752,7 +861,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           auto half_group = [&](int g16, int hf, bool padded) {
             float xo[8];
             float* px = xstate_ptr8(xs, g16, hf, r);
-            asm volatile("ld.global.cs.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+            asm volatile("ld.global" SDRM_ST_HINT ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=f"(xo[0]), "=f"(xo[1]), "=f"(xo[2]), "=f"(xo[3]), "=f"(xo[4]), "=f"(xo[5]), "=f"(xo[6]), "=f"(xo[7])
                          : "l"(px)
                          : "memory");
@@ -786,7 +895,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               for (int e = 0; e < 8; ++e)
                 if (f0 + e >= L) xo[e] = 0.0f;   // padding columns stay exactly 0
             }
-            asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+            asm volatile("st.global" SDRM_ST_HINT ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                          ::"l"(px), "f"(xo[0]), "f"(xo[1]), "f"(xo[2]), "f"(xo[3]), "f"(xo[4]), "f"(xo[5]), "f"(xo[6]), "f"(xo[7])
                          : "memory");
           };
@@ -799,7 +908,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           if (full_groups < Lg16) group(full_groups, true);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_noise_ready);
+        if (lane == 0) mbar_arrive(bar_noise_ready(s));
       }
     }
   }

@@ -106,6 +106,35 @@ def test_single_and_pair_mode_are_bit_identical():
         assert torch.equal(outs[1], outs[c]), c
 
 
+def test_interleaved_sub_tiles_are_bit_identical():
+    """A CTA pair that owns several row tiles interleaves two of them layer by layer (ChainParams::n_sub = 2, an odd last
+    tile runs alone); the grid cap makes a small launch take that path (12 row tiles on 2 pairs = 3 tiles per CTA)."""
+    from sdrm_b200 import _lib
+    lib = _lib.load()
+    n, I, H, L, T, nh, nd = 1500, 700, 200, 264, 7, 2, 1.0
+    diff, vae = random_modules(I, H, L, T, nh, seed=6, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    ref = eng.sample(n, seed=77, check=True).clone()
+    lat_ref = torch.empty(n, L, device="cuda")
+    eng.sample(n, seed=77, latent_out=lat_ref, check=True)
+    try:
+        for cluster, limit in ((2, 4), (2, 8), (4, 4)):
+            if lib.sdrm_resident_ctas(eng.handle, cluster) < cluster:
+                continue
+            lib.sdrm_set_cluster_override(cluster)
+            lib.sdrm_debug_set_grid_limit(limit)
+            for sub in (1, 2):
+                lib.sdrm_set_subtile_override(sub)
+                lat = torch.empty(n, L, device="cuda")
+                out = eng.sample(n, seed=77, latent_out=lat, check=True)
+                assert torch.equal(out, ref), (cluster, limit, sub)
+                assert torch.equal(lat, lat_ref), (cluster, limit, sub)
+    finally:
+        lib.sdrm_set_cluster_override(0)
+        lib.sdrm_debug_set_grid_limit(0)
+        lib.sdrm_set_subtile_override(0)
+
+
 def test_random_mode_matches_oracle():
     from oracle import philox_ref
     from oracle import sdrm_oracle as orc

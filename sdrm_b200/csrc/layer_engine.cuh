@@ -34,7 +34,12 @@ constexpr int M_WARP = W_WARP + 1;                 // UMMA issuer (also allocate
 constexpr int A_WARP = W_WARP + 2;                 // activation TMA producer
 // Register budget (setmaxnreg, per warpgroup): the kernel launches with 80 registers per thread (768 threads); the control
 // warpgroup drops to 40 and the noise warpgroup to 56 so that the four epilogue warpgroups can grow to 96.
-constexpr int REGS_CTRL = 48, REGS_NOISE = 48, REGS_EPI = 96;
+#ifndef SDRM_REGS_EPI
+#define SDRM_REGS_CTRL 48
+#define SDRM_REGS_NOISE 48
+#define SDRM_REGS_EPI 96
+#endif
+constexpr int REGS_CTRL = SDRM_REGS_CTRL, REGS_NOISE = SDRM_REGS_NOISE, REGS_EPI = SDRM_REGS_EPI;
 static_assert(128 * (REGS_CTRL + REGS_NOISE) + EPI_THREADS * REGS_EPI <= 80 * ENGINE_THREADS, "register pool");
 constexpr int ENGINE_SMEM_BYTES = 232448;          // all 227 KB: pair mode stages 7 x 32 KB, single mode 4 x 48 KB
 

@@ -35,16 +35,6 @@
 #ifndef SDRM_NSTG_PAIR
 #define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 (with 31 KB stages, MAX_NC = 240) measured no faster
 #endif
-#ifndef SDRM_DISCARD_DEAD
-#define SDRM_DISCARD_DEAD 0   // (measured slower, 312.9 vs 308.2 ms per cfg-5 shard: off) drop a chain layer's input images from L2 once its last UMMA has read them (no write-back of dead lines)
-#endif
-#ifndef SDRM_PREFETCH_STATE
-#define SDRM_PREFETCH_STATE 0 // L2 prefetch of the fp32 state columns one chunk ahead of the posterior epilogue (measured slower,
-                              // 302.9 vs 295.6 ms per cfg-5 shard: the earlier fills evict live activation lines; off)
-#endif
-#ifndef SDRM_DEFER_ALL
-#define SDRM_DEFER_ALL 1      // interleaved sub-tiles: every chunk is published one chunk late (no fence right behind its stores)
-#endif
 #ifndef SDRM_STATE_CS
 #define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
 #endif
@@ -457,23 +447,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       epi_bar_sync();
     }
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
-    uint32_t pending_bar = 0; // activation-chunk barrier whose publication (proxy fence + arrive) is deferred to the next chunk
-    auto publish_pending = [&]() {
-      if (pending_bar) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane0) mbar_arrive(pending_bar);
-        pending_bar = 0;
-        SDRM_TR_EPI(5);
-      }
-    };
     // context of the sub-tile a layer works on (set_ctx): scratch pointers are recomputed, the row facts are kept per sub-tile
     uint8_t* sc = nullptr;
     float* xs = nullptr;
     const uint16_t* mask_row = nullptr;
-    bool valid = false, valid0 = false, valid1 = false;
-    long long row = 0, row0 = 0, row1 = 0;
-    int t_row = 0, t_row0 = 0, t_row1 = 0;
+    bool valid = false;
+    long long row = 0;
+    int t_row = 0;
     for (; it < n_iters; ++it) {
       if (!PAIR && tile_of(it, 0) >= n_tiles) break;
       const int ns = nsub_of(it);
@@ -481,21 +461,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         sc = scratch_of(tile_of(it, s), s);
         xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
         mask_row = reinterpret_cast<const uint16_t*>(sc + P.mask_off + static_cast<size_t>(r) * P.mask_pitch);
-        valid = s ? valid1 : valid0;
-        row = s ? row1 : row0;
-        t_row = s ? t_row1 : t_row0;
+        // row facts are recomputed per layer (a handful of instructions, two cached loads in multi-resolution mode) rather
+        // than kept per sub-tile: the group loops have no register to spare
+        const long long prow = tile_of(it, s) * TILE_M + r;   // physical row of this launch
+        valid = prow < P.n_rows;
+        row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
+        t_row = P.T;
+        if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
       };
 
       // ---- row facts of every sub-tile; tile start step = max over rows (and sub-tiles)
       int m = 0;
       for (int s = 0; s < ns; ++s) {
-        const long long prow = tile_of(it, s) * TILE_M + r;   // physical row of this launch
-        const bool v = prow < P.n_rows;
-        const long long lrow = (v && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
-        int tr = P.T;
-        if (P.t_start) tr = v ? P.t_start[prow] : 0;
-        if (s == 0) { valid0 = v; row0 = lrow; t_row0 = tr; } else { valid1 = v; row1 = lrow; t_row1 = tr; }
-        m = max(m, tr);
+        set_ctx(s);
+        m = max(m, t_row);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -562,8 +541,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       if (lane == 0) mbar_arrive(bar_tile_ready);
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
-      auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s, int dead_buf, bool pf_next) {
+      auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) {
         constexpr int KIND = decltype(kind_c)::value;
+        // The LAST reverse step hands x_0 to the decoder as bf16 hi/lo images (and to x0_out).  That conversion runs as a
+        // separate pass over the finished fp32 state after the layer (once per tile), NOT inside the group loop: with both
+        // paths in the loop ptxas spilled loop invariants, and a spill reload issued behind the state loads of the next group
+        // returns only after them (in-order L1 return): 60 % of the posterior loop's stall samples (r01b profile).
+        const bool last_step = (KIND == EPI_POSTERIOR) && step == 1;
         uint8_t* out_hi_row = sc + static_cast<size_t>(out_hi_buf) * P.act_buf_bytes + row_off;
         uint8_t* out_lo_row = sc + static_cast<size_t>(out_lo_buf) * P.act_buf_bytes + row_off;
         const float* bias_row = ld.bias + static_cast<size_t>(step) * ld.bias_step_stride;
@@ -583,26 +567,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         }
         const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
-        const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT;
-        // With a second sub-tile in flight the next layer of THIS tile is a whole layer away: every chunk is published one
-        // chunk late, so that no fence.proxy.async sits right behind its own stores (the membar inside it waits for them to
-        // reach L2: 10 % of the epilogue warps' time in the r01 profile).  A tile running alone publishes its last two
-        // chunks right away: the next layer's tail k-blocks wait for them.
-        const bool defer_all = SDRM_DEFER_ALL && ns > 1;
-        // L2 prefetch of the state columns this warp's groups of posterior chunk c touch (64 lines of 128 B: 4 groups x 2
-        // halves x 1 KB): the state streams through HBM between steps, and with only one group requested ahead every group of
-        // the posterior epilogue waited out a DRAM round trip (its chunks took 2x as long as their UMMAs).
-        auto prefetch_state = [&](int g16_base, int ng) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int li = lane + 32 * k;
-            const int g = sub + EPI_SUB * (li >> 4);
-            if (g < ng && g16_base + g < P.Lg16) {
-              const uint8_t* pl = reinterpret_cast<const uint8_t*>(xstate_ptr8(xs, g16_base + g, (li >> 3) & 1, q * 32)) + (li & 7) * 128;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(pl));
-            }
-          }
-        };
+        const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step;
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
         // warp stages the 64 floats of its own groups of a chunk in a private shared-memory slice (lane l holds elements
         // 2l, 2l+1: group slot l / 8, columns 2 (l % 8) ..) one chunk ahead, and the group loop reads them with LDS.128.
@@ -629,34 +594,28 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             const int g16 = (fc >> 4) + g;
             if (g16 < P.Lg16) {
               xs_load16(xs, g16, r, xn);
-              if (step > 1) keep = mask_row[g16];
+              keep = mask_row[g16];   // (stale at the last step: its dropout output is overwritten by the x_0 pass)
             }
           };
           // does not depend on the accumulator: ask before waiting (first chunk only: later chunks fence first, and a membar
           // would wait for these loads to return)
           if (KIND == EPI_POSTERIOR && c == 0 && sub < ngroups) request_state(sub);
-          if (SDRM_PREFETCH_STATE) {
-            if (KIND == EPI_POSTERIOR && c + 1 < NCH) prefetch_state(((c + 1) * NC) >> 4, ngroups);
-            if (KIND != EPI_POSTERIOR && pf_next && c == NCH - 1) prefetch_state(0, P.step[P.n_step - 1].NC >> 4);
-          }
           SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          if (SDRM_DISCARD_DEAD && dead_buf >= 0 && c == NCH - 1) {
-            // The layer's last UMMA has completed, so every TMA read of its input images is done and nothing reads them
-            // again: the next layer of this tile overwrites that buffer.  Dropping the (dirty) lines from L2 now saves their
-            // write-back to HBM (1.44 MB per tile and step at cfg 5, 40 % of the kernel's DRAM traffic) and frees L2
-            // capacity for the live buffers.  Thread (row r, sub) drops the 128-byte row r of k-blocks sub, sub + 4, ...
-            uint8_t* drow = sc + static_cast<size_t>(dead_buf) * P.act_buf_bytes + row_off;
-            for (int kb = sub; kb < ld.KB; kb += EPI_SUB)
-              asm volatile("discard.global.L2 [%0], 128;" ::"l"(drow + static_cast<size_t>(kb) * A_TILE_BYTES) : "memory");
+          if (c > 0 && c < NCH - 1 && publishes) {   // chunk c-1 <= NCH-3
+            // Deferred publication of the PREVIOUS chunk (same layer): its stores were issued a whole accumulator wait ago, so
+            // the membar inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only
+            // the next layer reads these activations and it cannot finish its first chunk before this layer's last one.
+            // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The LAST
+            // chunk's epilogue is the critical path of the layer boundary (timeline: the next layer's first chunk takes twice
+            // as long as the others), so nothing is deferred into it.
+            fence_proxy_async();
+            __syncwarp();
+            if (lane0) mbar_arrive(bar_act_chunk(s, c - 1));
+            SDRM_TR_EPI(5);
           }
-          // Deferred publication of the PREVIOUS chunk: its stores were issued a whole accumulator wait ago, so the membar
-          // inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only the next
-          // layer reads these activations and it cannot finish its first chunk before this layer's last one.
-          // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)
-          publish_pending();
           if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
           if (KIND == EPI_POSTERIOR && c > 0 && sub < ngroups) request_state(sub);
           if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
@@ -674,7 +633,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
               h[4 * j] = lo.x; h[4 * j + 1] = lo.y; h[4 * j + 2] = hi.x; h[4 * j + 3] = hi.y;
             }
-            if (g + EPI_SUB < ngroups) tmem_ld16(t_chunk + (g + EPI_SUB) * 16u, v);
+            // (posterior update: the next group's accumulator columns are requested at the END of the iteration instead: with
+            // v[] live across the update the loop spilled its invariants, and a spill reload queued behind the state loads of
+            // the next group returns only after them (in-order L1 return) -- 60 % of this loop's stall samples in the r01 profile)
+            if (KIND != EPI_POSTERIOR && g + EPI_SUB < ngroups) tmem_ld16(t_chunk + (g + EPI_SUB) * 16u, v);
             if (KIND == EPI_PRELU) {
               uint32_t pk[8];
               if (slope01) {
@@ -705,29 +667,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   xn[2 * e] = nv.x; xn[2 * e + 1] = nv.y;
                 }
                 xs_store16(xs, g16, r, xn);
-                if (step > 1) {
+                {
                   uint32_t pk[8];
                   dropout_pack(xn, keep, pk);
                   store_act(out_hi_row, f0, pk);
-                } else {
-                  // last reverse step: hand x_0 to the decoder as bf16 hi/lo (bf16x3 GEMM)
-                  uint32_t ph[8], pl[8];
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) {
-                    const float h0 = bf16_round(xn[2 * e]), h1 = bf16_round(xn[2 * e + 1]);
-                    ph[e] = pack_bf16x2(h0, h1);
-                    pl[e] = pack_bf16x2(xn[2 * e] - h0, xn[2 * e + 1] - h1);
-                  }
-                  store_act(out_hi_row, f0, ph);
-                  store_act(out_lo_row, f0, pl);
-                  if (P.x0_out && valid) {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e)
-                      if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = xn[e];
-                  }
                 }
                 if (g + EPI_SUB < ngroups) request_state(g + EPI_SUB);   // xn is dead: fetch the next group's state columns
               }
+              if (g + EPI_SUB < ngroups) tmem_ld16(t_chunk + (g + EPI_SUB) * 16u, v);
             } else if (KIND == EPI_TANH_SPLIT) {
               uint32_t ph[8], pl[8];
 #pragma unroll
@@ -764,35 +711,67 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
           // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
-          if (publishes) {
-            pending_bar = bar_act_chunk(s, c);
-            if (!defer_all && c >= NCH - 2) publish_pending();
+          if (publishes && c >= NCH - 2) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane0) mbar_arrive(bar_act_chunk(s, c));
+            SDRM_TR_EPI(5);
           }
         }
-        if (KIND == EPI_POSTERIOR && step > 1) {
+        if (KIND == EPI_POSTERIOR && last_step) {
+          // x_0 pass: every thread re-reads the state columns it wrote itself (same chunk / group ownership as above)
+          for (int c = 0; c < NCH; ++c)
+            for (int g = sub; g < ngroups; g += EPI_SUB) {
+              const int g16 = ((c * NC) >> 4) + g;
+              if (g16 >= P.Lg16) continue;
+              const int f0 = g16 * 16;
+              float x0v[16];
+              xs_load16(xs, g16, r, x0v);
+              uint32_t ph[8], pl[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float h0 = bf16_round(x0v[2 * e]), h1 = bf16_round(x0v[2 * e + 1]);
+                ph[e] = pack_bf16x2(h0, h1);
+                pl[e] = pack_bf16x2(x0v[2 * e] - h0, x0v[2 * e + 1] - h1);
+              }
+              store_act(out_hi_row, f0, ph);
+              store_act(out_lo_row, f0, pl);
+              if (P.x0_out && valid) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = x0v[e];
+              }
+            }
+          if (!last_of_tile) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane0)
+              for (int c = 0; c < NCH; ++c) mbar_arrive(bar_act_chunk(s, c));
+          }
+        }
+        if (KIND == EPI_POSTERIOR && !last_step) {
           __syncwarp();
           if (lane0) mbar_arrive(bar_state_ready(s));   // x_{i-1} is complete: the noise warps may prepare step i-1
         }
       };
-      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s, int dead_buf, bool pf_next) {
+      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) {
         set_ctx(s);
         switch (ld.kind) {
-          case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, pf_next); break;
-          case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
-          case EPI_TANH_SPLIT: run(std::integral_constant<int, EPI_TANH_SPLIT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
-          default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s, dead_buf, false); break;
+          case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
+          case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
+          case EPI_TANH_SPLIT: run(std::integral_constant<int, EPI_TANH_SPLIT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
+          default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
         }
       };
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
         for (int l = 0; l < P.n_step; ++l) {
           for (int s = 0; s < ns; ++s)
-            run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2, s, cur, l == P.n_step - 2);   // x0 lo -> buffer 2; input = cur
+            run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2, s);   // x0 lo -> buffer 2
           cur ^= 1;
         }
       for (int l = 0; l < P.n_dec; ++l)
-        for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s, -1, false);
-      publish_pending();
+        for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s);
     }
   } else {
     // ======================================= noise warps ========================================

@@ -35,6 +35,9 @@
 #ifndef SDRM_NSTG_PAIR
 #define SDRM_NSTG_PAIR 6   // pair-mode pipeline depth (32 KB stages); 7 (with 31 KB stages, MAX_NC = 240) measured no faster
 #endif
+#ifndef SDRM_POSTERIOR_MUFU_TANH
+#define SDRM_POSTERIOR_MUFU_TANH 1   // eps = tanh.approx.f32 (1 MUFU instead of ex2 + rcp + 3 FP ops) in the posterior update
+#endif
 #ifndef SDRM_STATE_CS
 #define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
 #endif
@@ -593,8 +596,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           auto request_state = [&](int g) {
             const int g16 = (fc >> 4) + g;
             if (g16 < P.Lg16) {
+              keep = mask_row[g16];   // first: loads return in order, and this one hits L1/L2 (stale at the last step: its
+                                      // dropout output is overwritten by the x_0 pass)
               xs_load16(xs, g16, r, xn);
-              keep = mask_row[g16];   // (stale at the last step: its dropout output is overwritten by the x_0 pass)
             }
           };
           // does not depend on the accumulator: ask before waiting (first chunk only: later chunks fence first, and a membar
@@ -604,16 +608,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          if (c > 0 && c < NCH - 1 && publishes) {   // chunk c-1 <= NCH-3
-            // Deferred publication of the PREVIOUS chunk (same layer): its stores were issued a whole accumulator wait ago, so
-            // the membar inside fence.proxy.async does not also wait for them, and it is off the layer's critical path.  Only
-            // the next layer reads these activations and it cannot finish its first chunk before this layer's last one.
-            // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The LAST
-            // chunk's epilogue is the critical path of the layer boundary (timeline: the next layer's first chunk takes twice
-            // as long as the others), so nothing is deferred into it.
+          if (c > 0 && c == NCH - 2 && publishes) {
+            // Deferred publication of ALL earlier chunks (0 .. NCH-3) with ONE proxy fence: their stores were issued at least
+            // a whole accumulator wait ago, and only the next layer reads these activations -- it cannot issue its first UMMA
+            // before this layer's last chunk is in the tensor pipe.  (A fence.proxy.async is a membar.gpu round trip of ~1.3 us
+            // per warp whatever is outstanding -- r01c profile -- so the epilogue pays three per layer instead of four.)
+            // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The last two
+            // chunks are published right behind their stores: the next layer's tail k-blocks wait for them.
             fence_proxy_async();
             __syncwarp();
-            if (lane0) mbar_arrive(bar_act_chunk(s, c - 1));
+            if (lane0)
+              for (int cp = 0; cp < c; ++cp) mbar_arrive(bar_act_chunk(s, cp));
             SDRM_TR_EPI(5);
           }
           if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
@@ -624,11 +629,16 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           for (int g = sub; g < ngroups; g += EPI_SUB, bs += 4) {
             const int f0 = fc + g * 16;
             const int g16 = f0 >> 4;
+            // bias first: the LDS latency (long while the UMMAs and the TMA keep shared memory busy) overlaps the TMEM wait
+            // instead of following it (r01c profile: 27 % + 25 % of the PReLU loop's samples were these two waits back to back)
+            float4 b4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b4[j] = bs[j];
             tmem_ld_wait();
             float h[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 b = bs[j];
+              const float4 b = b4[j];
               const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])), make_float2(b.x, b.y));
               const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])), make_float2(b.z, b.w));
               h[4 * j] = lo.x; h[4 * j + 1] = lo.y; h[4 * j + 2] = hi.x; h[4 * j + 3] = hi.y;
@@ -663,7 +673,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 const float2 nc = make_float2(-c12, -c12);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
+#if SDRM_POSTERIOR_MUFU_TANH
+                  const float2 nv = __ffma2_rn(nc, make_float2(mufu_tanh(h[2 * e]), mufu_tanh(h[2 * e + 1])), make_float2(xn[2 * e], xn[2 * e + 1]));
+#else
                   const float2 nv = __ffma2_rn(nc, make_float2(fast_tanh(h[2 * e]), fast_tanh(h[2 * e + 1])), make_float2(xn[2 * e], xn[2 * e + 1]));
+#endif
                   xn[2 * e] = nv.x; xn[2 * e + 1] = nv.y;
                 }
                 xs_store16(xs, g16, r, xn);

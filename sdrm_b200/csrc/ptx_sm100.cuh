@@ -306,6 +306,12 @@ __device__ __forceinline__ float fast_tanh(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return fmaf(-2.0f, r, 1.0f);
 }
+// one MUFU op (tanh.approx.f32, max abs error 2^-10.99): only where the result is scaled by a small coefficient
+__device__ __forceinline__ float mufu_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // keep a loop-invariant value in its register: without this ptxas re-derives thread-index based values with S2R
 // (a ~20-cycle short-scoreboard stall) inside the hottest loops
 __device__ __forceinline__ void pin_reg(uint32_t& v) { asm volatile("" : "+r"(v)); }

@@ -97,7 +97,8 @@ __global__ void pack_act_kernel(const float* __restrict__ A, long long M, int K,
       lo[e] = pack_bf16x2(v0 - h0, v1 - h1);
     }
     uint8_t* base = scratch + static_cast<size_t>(tile) * scratch_stride;
-    const size_t off = static_cast<size_t>(kb) * A_TILE_BYTES + r * 128 + ((j ^ (r & 7)) << 4);
+    // activation images are LINEAR in global memory ([k block][row][64 bf16]); the TMA load swizzles them (SWIZZLE_128B)
+    const size_t off = static_cast<size_t>(kb) * A_TILE_BYTES + r * 128 + (j << 4);
     *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(base + act_buf_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
@@ -259,15 +260,16 @@ static EncodeTiledFn get_encode_fn() {
   fn = reinterpret_cast<EncodeTiledFn>(p);
   return fn;
 }
-static int make_rows_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned box_rows) {
+static int make_rows_map(CUtensorMap* map, const void* base, unsigned long long rows, unsigned box_rows, unsigned box_bytes = 128,
+                         bool swizzle128 = false) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return sdrm_fail(SDRM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t dims[2] = {128, rows};
   const cuuint64_t strides[1] = {128};
-  const cuuint32_t box[2] = {128, box_rows};
+  const cuuint32_t box[2] = {box_bytes, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char msg[128];
@@ -275,6 +277,13 @@ static int make_rows_map(CUtensorMap* map, const void* base, unsigned long long 
     return sdrm_fail(SDRM_ERR_CUDA, msg);
   }
   return SDRM_OK;
+}
+// Activation scratch maps (every mode): the images are linear rows of 128 bytes; loads take a 128-row box and swizzle it into the
+// UMMA operand layout, the epilogue stores 32 rows x 32 bytes (one warp's 16-column group) from a dense shared-memory box
+static int fill_act_maps(ChainParams& P, size_t workspace_bytes) {
+  int rc = make_rows_map(&P.tm_act, P.scratch, workspace_bytes / 128, TILE_M, 128, true);
+  if (rc) return rc;
+  return make_rows_map(&P.tm_act_st, P.scratch, workspace_bytes / 128, 32, 32, false);
 }
 static int fill_pair_maps(ChainParams& P, size_t workspace_bytes, int cluster) {
   auto w_rows = [](const LayerDesc& d) {
@@ -288,7 +297,8 @@ static int fill_pair_maps(ChainParams& P, size_t workspace_bytes, int cluster) {
     int rc = make_rows_map(&P.tm_dec_w[l], P.dec[l].w_img, w_rows(P.dec[l]), P.dec[l].NC / cluster);
     if (rc) return rc;
   }
-  return make_rows_map(&P.tm_act, P.scratch, workspace_bytes / 128, TILE_M);
+  (void)workspace_bytes;
+  return SDRM_OK;
 }
 
 static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st) {
@@ -539,6 +549,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   }
   if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
   h->last_cluster = cluster;
+  rc = fill_act_maps(P, static_cast<size_t>(grid) * stride);
+  if (rc) return rc;
   if (cluster >= 2) {
     rc = fill_pair_maps(P, static_cast<size_t>(grid) * stride, cluster);
     if (rc) return rc;
@@ -640,6 +652,8 @@ int sdrm_probe_linear(const float* d_A, const float* d_W, const float* d_bias, f
   P.scratch = ws + s_off; P.scratch_stride = 2 * act; P.act_buf_bytes = act;
   P.err_word = reinterpret_cast<int*>(ws);
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, sms)));
+  rc = fill_act_maps(P, static_cast<size_t>(n_tiles) * 2 * act);
+  if (rc) return rc;
   for (int rep = 0; rep < g_probe_repeat; ++rep) {
     rc = launch_engine(P, grid, 1, st);
     if (rc) return rc;

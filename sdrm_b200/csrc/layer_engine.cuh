@@ -92,7 +92,8 @@ struct ChainParams {
   // activation scratch (box = 128 rows); tensor-map loads may complete on the LEADER CTA's mbarrier (.cta_group::2)
   CUtensorMap tm_step_w[MAX_STEP_LAYERS];
   CUtensorMap tm_dec_w[2];
-  CUtensorMap tm_act;
+  CUtensorMap tm_act;       // loads: box 128 B x 128 rows, SWIZZLE_128B (linear global rows -> UMMA operand layout)
+  CUtensorMap tm_act_st;    // epilogue stores: box 32 B x 32 rows, no swizzle
   int debug_flags;            // perf experiments only (-DSDRM_PERF_DEBUG builds): 1 = skip activation stores, 4 = skip noise; 8 = trace k-blocks
   unsigned long long* trace;  // debug: [3 roles][TRACE_CAP] (event code << 56 | globaltimer ns), CTA 0 only; or nullptr
 };

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr uint32_t BIAS_SLICE_BYTES = 4 * 16 * 4;   // per epilogue warp: the bias of its (at most 4) column groups of one chunk
   constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 2);   // mbarriers of a CTA (map below)
-  static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * BIAS_SLICE_BYTES + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
+  constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // per epilogue warp: one 16-column group of its 32 rows, dense bf16 (TMA store box)
+  static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -135,6 +136,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
   uint8_t* bias_slices = smem + ((NSTG * STG_BYTES + 8 * NBAR + 16 + 8 * EPI_WARPS + 15) & ~15);   // EPI_WARPS x BIAS_SLICE_BYTES, 16-byte aligned
+  const uint32_t out_slots = (smem_u32(bias_slices) + EPI_WARPS * BIAS_SLICE_BYTES + 127u) & ~127u;   // EPI_WARPS x OUT_SLOT_BYTES, 128-byte aligned
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   bulk_g2s_hint(stage_w(stage), w_src, w_bytes, fb, pol_keep);
                 } else {
                   mbar_arrive_expect_tx(fb, A_TILE_BYTES);
-                  bulk_g2s_hint(stage_a(stage), a_src, A_TILE_BYTES, fb, pol_keep);
+                  tma_load_2d_hint(stage_a(stage), &P.tm_act, 0, a_row, fb, pol_keep);
                 }
               }
               __syncwarp();
@@ -412,21 +414,38 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     uint32_t lane0 = (lane == 0) ? 1u : 0u;
     pin_reg(lane0); pin_reg(lane_addr);
     const uint32_t row_off = static_cast<uint32_t>(r) * 128u;
-    const uint32_t swz = static_cast<uint32_t>(r & 6) << 4;   // 128-byte swizzle of the row, 32-byte-sector part
-    const bool flip = r & 1;                                  // odd rows hold the two 16-byte pieces of a sector swapped
     float* bias_s = reinterpret_cast<float*>(bias_slices + warp * BIAS_SLICE_BYTES);   // this warp's private bias slice
     uint32_t cc = 0;
     int it = 0;
 
-    // write 16 consecutive bf16 features [f0, f0+16) of this thread's row into a k-block image buffer: ONE 256-bit store
-    // (the stores scatter over 32 rows per warp, so their count is what costs)
+    // Write 16 consecutive bf16 features [f0, f0+16) of the warp's 32 rows into a k-block image: the lanes drop their 32 bytes
+    // into the warp's dense shared-memory slot and lane 0 hands the 32 x 32-byte box to the TMA (tensor-map store into the
+    // linear activation image; the TMA LOAD swizzles it into the UMMA operand layout).  Against 256-bit global stores
+    // scattered over 32 rows this frees the source registers at once (the next iteration's loads waited for the LSU to dequeue
+    // the store: 27 % of the PReLU loop's samples), needs no swizzle shuffles, and the writes stay in the async proxy, so
+    // publishing a chunk is a bulk-group wait of one lane instead of a membar.gpu + proxy fence of every thread.
+    const uint32_t out_slot = out_slots + static_cast<uint32_t>(warp) * OUT_SLOT_BYTES;
+    const uint32_t out_lane = out_slot + static_cast<uint32_t>(lane) * 32u;
     auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
-      uint8_t* sector = buf_row + static_cast<size_t>(f0 >> 6) * A_TILE_BYTES + ((static_cast<uint32_t>(f0 & 48) << 1) ^ swz);
-      const uint32_t a0 = flip ? pk[4] : pk[0], a1 = flip ? pk[5] : pk[1], a2 = flip ? pk[6] : pk[2], a3 = flip ? pk[7] : pk[3];
-      const uint32_t b0 = flip ? pk[0] : pk[4], b1 = flip ? pk[1] : pk[5], b2 = flip ? pk[2] : pk[6], b3 = flip ? pk[3] : pk[7];
-      asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
-                   ::"l"(sector), "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(b2), "r"(b3), "l"(pol_keep)
-                   : "memory");
+      // (elect.sync with a full mask always names the same lane; converged single-lane issue keeps ptxas from wrapping the
+      // uniform-datapath TMA instruction in an elect loop)
+      if (elect_one()) bulk_wait_group_read<0>();   // the previous box has been read out of the slot
+      __syncwarp();
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      // first row of the box = row 32 q of the tile (lane 0's buf_row)
+      const int y = __shfl_sync(0xffffffffu, static_cast<int>((buf_row - P.scratch) >> 7), 0) + (f0 >> 6) * TILE_M;
+      if (elect_one()) {
+        tma_store_2d_hint(&P.tm_act_st, (f0 & 63) * 2, y, out_slot, pol_keep);
+        bulk_commit_group();
+      }
+    };
+    // all TMA stores of this warp have been written (lane 0 issued them): what a chunk / tile publication waits for
+    auto stores_done = [&]() {
+      if (elect_one()) bulk_wait_group<0>();
+      __syncwarp();
     };
     // dropout (F.dropout p = .5: kept values are doubled) + bf16 pack of 16 state values
     auto dropout_pack = [&](const float (&x)[16], uint32_t keep, uint32_t (&pk)[8]) {
@@ -539,8 +558,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         }
       }
       if (warp == 0 && lane == 0) tile_T[it & 1] = T_tile;
-      fence_proxy_async();
-      __syncwarp();
+      fence_proxy_async();   // the zero fill of the buffers (generic stores) is read by the TMA loads too
+      stores_done();
       if (lane == 0) mbar_arrive(bar_tile_ready);
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
@@ -615,8 +634,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             // per warp whatever is outstanding -- r01c profile -- so the epilogue pays three per layer instead of four.)
             // (Issued before the TMEM load: with the accumulator registers live across the fence ptxas spills.)  The last two
             // chunks are published right behind their stores: the next layer's tail k-blocks wait for them.
-            fence_proxy_async();
-            __syncwarp();
+            stores_done();
             if (lane0)
               for (int cp = 0; cp < c; ++cp) mbar_arrive(bar_act_chunk(s, cp));
             SDRM_TR_EPI(5);
@@ -726,8 +744,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
           // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
           if (publishes && c >= NCH - 2) {
-            fence_proxy_async();
-            __syncwarp();
+            stores_done();
             if (lane0) mbar_arrive(bar_act_chunk(s, c));
             SDRM_TR_EPI(5);
           }
@@ -757,8 +774,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               }
             }
           if (!last_of_tile) {
-            fence_proxy_async();
-            __syncwarp();
+            stores_done();
             if (lane0)
               for (int c = 0; c < NCH; ++c) mbar_arrive(bar_act_chunk(s, c));
           }

@@ -152,6 +152,20 @@ __device__ __forceinline__ void tma_load_2d_pair_mcast_hint(uint32_t dst, const 
       ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask), "l"(pol)
       : "memory");
 }
+// 2-D tensor-map load into this CTA's shared memory, completion on a local mbarrier (single-CTA mode)
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "l"(pol)
+      : "memory");
+}
+// 2-D tensor-map store shared -> global (bulk async-group completion: bulk_commit_group / bulk_wait_group[_read])
+__device__ __forceinline__ void tma_store_2d_hint(const void* tmap, int c0, int c1, uint32_t src_smem, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+      ::"l"(tmap), "r"(c0), "r"(c1), "r"(src_smem), "l"(pol)
+      : "memory");
+}
 // 1-D bulk copy global -> shared, completion on a local mbarrier (plain form: used by the microbenchmarks in tools/)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar) {
   asm volatile(

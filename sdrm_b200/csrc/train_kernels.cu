@@ -39,7 +39,51 @@ __global__ void __launch_bounds__(256) noise_inputs_kernel(
   const bool aligned = ((g0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(mu) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(in_pert) & 15) == 0) && ((reinterpret_cast<uintptr_t>(in_clean) & 15) == 0) &&
                        ((reinterpret_cast<uintptr_t>(in_shift) & 15) == 0) && (!noise_out || (reinterpret_cast<uintptr_t>(noise_out) & 15) == 0);
+  const bool fast_ok = aligned && !inj_masks && !inj_noise && !masks_out && L >= 4 && total <= 0x7fffffffLL;
   for (unsigned long long blk = first_blk + warp; blk < last_blk; blk += n_warps) {
+    // Interior blocks (all 512 elements inside the local range, 16-byte aligned, in-kernel streams): the same arithmetic as the
+    // general path below without its per-element range / alignment / injection branches (2/3 of its issued instructions)
+    if (fast_ok && blk * 512ull >= g0 && blk * 512ull + 512ull <= g0 + static_cast<unsigned long long>(total)) {
+      const unsigned long long mc = blk * 32ull + lane;
+      const u32x4 m4 = philox4x32_10_keys(static_cast<uint32_t>(mc), static_cast<uint32_t>(mc >> 32), 0u, STREAM_TRAIN_MASK, K);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned long long gq = blk * 128ull + static_cast<unsigned long long>(j * 32 + lane);
+        const uint32_t i0 = static_cast<uint32_t>(gq * 4ull - g0);
+        const float4 v = *reinterpret_cast<const float4*>(mu + i0);
+        const u32x4 r4 = philox4x32_10_keys(static_cast<uint32_t>(gq), static_cast<uint32_t>(gq >> 32), 0u, STREAM_TRAIN_NOISE, K);
+        float nz[4];
+        box_muller_fast(r4.x, r4.y, nz[0], nz[1]);
+        box_muller_fast(r4.z, r4.w, nz[2], nz[3]);
+        const uint32_t b0 = i0 / static_cast<uint32_t>(L);
+        const int f_first = static_cast<int>(i0 - b0 * static_cast<uint32_t>(L));
+        const float abt0 = __ldg(ab + __ldg(t + b0));
+        float sa0 = sqrtf(abt0), om0 = 1.0f - abt0, sa1 = sa0, om1 = om0;
+        if (f_first + 3 >= L && static_cast<long long>(b0) + 1 < B) {
+          const float abt1 = __ldg(ab + __ldg(t + b0 + 1));
+          sa1 = sqrtf(abt1); om1 = 1.0f - abt1;
+        }
+        const float m[4] = {v.x, v.y, v.z, v.w};
+        float xp[4], xc[4], xs[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          nz[e] *= nd;
+          const bool second = f_first + e >= L;
+          const float sa = second ? sa1 : sa0, om = second ? om1 : om0;
+          const int bit = 4 * j + e;
+          const float xt = sa * m[e] + om * nz[e];
+          const float xq = m[e] + mu_coef * nz[e];
+          xp[e] = ((m4.x >> bit) & 1u) ? 2.0f * xt : 0.0f;
+          xc[e] = ((m4.y >> bit) & 1u) ? 2.0f * m[e] : 0.0f;
+          xs[e] = ((m4.z >> bit) & 1u) ? 2.0f * xq : 0.0f;
+        }
+        if (noise_out) __stcs(reinterpret_cast<float4*>(noise_out + i0), make_float4(nz[0], nz[1], nz[2], nz[3]));
+        __stcs(reinterpret_cast<float4*>(in_pert + i0), make_float4(xp[0], xp[1], xp[2], xp[3]));
+        __stcs(reinterpret_cast<float4*>(in_clean + i0), make_float4(xc[0], xc[1], xc[2], xc[3]));
+        __stcs(reinterpret_cast<float4*>(in_shift + i0), make_float4(xs[0], xs[1], xs[2], xs[3]));
+      }
+      continue;
+    }
     uint32_t keep[3] = {0u, 0u, 0u};
     if (!inj_masks) {
       const unsigned long long mc = blk * 32ull + lane;
@@ -75,17 +119,41 @@ __global__ void __launch_bounds__(256) noise_inputs_kernel(
       }
       // rows of the four elements (a quad straddles two rows when L % 4 != 0)
       const long long ic = i0 < 0 ? 0 : i0;
-      const long long b0 = ic / L;
-      const int f_first = static_cast<int>(ic - b0 * L);
+      long long b0;
+      int f_first;
+      if (total <= 0x7fffffffLL) {   // 32-bit division: the 64-bit one costs more than the quad's Philox call
+        const uint32_t q32 = static_cast<uint32_t>(ic) / static_cast<uint32_t>(L);
+        b0 = q32;
+        f_first = static_cast<int>(static_cast<uint32_t>(ic) - q32 * static_cast<uint32_t>(L));
+      } else {
+        b0 = ic / L;
+        f_first = static_cast<int>(ic - b0 * L);
+      }
+      // schedule coefficients of the (at most two, for L >= 4) rows the quad touches: looked up once per row, not per element
+      float sa0, om0, sa1, om1;
+      {
+        const float abt0 = __ldg(ab + __ldg(t + b0));
+        sa0 = sqrtf(abt0); om0 = 1.0f - abt0;
+        sa1 = sa0; om1 = om0;
+        if (L >= 4 && f_first + 3 >= L && b0 + 1 < B) {
+          const float abt1 = __ldg(ab + __ldg(t + b0 + 1));
+          sa1 = sqrtf(abt1); om1 = 1.0f - abt1;
+        }
+      }
       float xp[4], xc[4], xs[4];
       uint32_t kb[3] = {0u, 0u, 0u};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         if (!ok[e]) { xp[e] = xc[e] = xs[e] = 0.f; continue; }
         const long long ie = i0 + e;
-        const long long be = (L >= 4) ? b0 + ((f_first + static_cast<int>(ie - ic)) >= L ? 1 : 0) : ie / L;
-        const float abt = __ldg(ab + __ldg(t + be));
-        const float sa = sqrtf(abt), om = 1.0f - abt;
+        float sa, om;
+        if (L >= 4) {
+          const bool second = (f_first + static_cast<int>(ie - ic)) >= L;
+          sa = second ? sa1 : sa0; om = second ? om1 : om0;
+        } else {
+          const float abt = __ldg(ab + __ldg(t + ie / L));
+          sa = sqrtf(abt); om = 1.0f - abt;
+        }
         const int bit = 4 * j + e;
         if (inj_masks) {
 #pragma unroll

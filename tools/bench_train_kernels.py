@@ -63,3 +63,14 @@ xs = (torch.rand(8192, 20000, device="cuda") < 0.01).float().to_sparse_csr()
 nnz = xs.values().numel()
 ms = timed(lambda: enc.hidden(xs))
 line(f"encode_csr 8192 rows, nnz {nnz}, H 1000 (gather bytes)", ms, 4.0 * nnz * 1000)
+
+# K3: warp top-k over a score matrix (4 bytes read per score)
+from sdrm_b200 import metrics
+del logits, X, grad, mu, pred, sxx, psx
+torch.cuda.empty_cache()
+for rows, items in ((65536, 20000), (9558, 8582)):
+    sc = torch.randn(rows, items, device="cuda")
+    for k in (10, 50):
+        ms = timed(lambda: metrics.topk_device(sc, k))
+        print(f"K3 topk k={k:<2d} {rows}x{items} fp32".ljust(47), f"{ms:8.3f} ms  {4.0 * rows * items / ms / 1e6:8.1f} GB/s  {4.0 * rows * items / ms / 1e6 / peak:5.2f} of measured HBM peak ({peak} GB/s)")
+    del sc

@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint3
 // bits[row][w] bit j = (score[row][32 w + j] >= thr)  (mode 0)  or  <= thr (mode 1).  A warp walks whole rows: every lane
 // loads 4 consecutive scores (a 512-byte coalesced warp load, two in flight), forms its 4-bit nibble and three xor-shuffles
 // assemble the four 32-bit words of the 128 columns.
-__global__ void __launch_bounds__(256) threshold_pack_kernel(MatView m, float thr, int mode, uint32_t* __restrict__ bits,
+template <int MODE>
+__global__ void __launch_bounds__(256) threshold_pack_kernel(MatView m, float thr, uint32_t* __restrict__ bits,
                                                              long long words_per_row, unsigned long long* __restrict__ count) {
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
@@ -111,11 +112,31 @@ __global__ void __launch_bounds__(256) threshold_pack_kernel(MatView m, float th
   const bool vec = ((m.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.x) & 15) == 0);
   const int n_cols = m.n_cols;
   unsigned long long ones = 0;
-  auto hit = [&](float v) { return mode == 0 ? (v >= thr) : (v <= thr); };
+  auto hit = [&](float v) { return MODE == 0 ? (v >= thr) : (v <= thr); };
   for (long long r = warp; r < m.rows; r += n_warps) {
     const float* x = m.x + r * m.ld;
     uint32_t* out = bits + r * words_per_row;
-    for (int c0 = 0; c0 < n_cols; c0 += 256) {
+    int c0 = 0;
+    // interior: whole 512-column spans of 16-byte aligned rows, four loads in flight per lane, no per-element range checks
+    if (vec) {
+      for (; c0 + 512 <= n_cols; c0 += 512) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(x + c0 + u * 128 + lane * 4));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          uint32_t w = ((hit(v[u].x) ? 1u : 0u) | (hit(v[u].y) ? 2u : 0u) | (hit(v[u].z) ? 4u : 0u) | (hit(v[u].w) ? 8u : 0u)) << (4 * (lane & 7));
+          w |= __shfl_xor_sync(0xffffffffu, w, 1);
+          w |= __shfl_xor_sync(0xffffffffu, w, 2);
+          w |= __shfl_xor_sync(0xffffffffu, w, 4);
+          if ((lane & 7) == 0) {
+            out[(c0 + u * 128) / 32 + (lane >> 3)] = w;
+            ones += __popc(w);
+          }
+        }
+      }
+    }
+    for (; c0 < n_cols; c0 += 256) {
       uint32_t nib[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -202,7 +223,8 @@ int sdrm_threshold_pack(const float* d_scores, int64_t rows, int n_cols, int64_t
   if (mode == 0 && static_cast<double>(tf) < threshold) tf = nextafterf(tf, INFINITY);
   if (mode == 1 && static_cast<double>(tf) > threshold) tf = nextafterf(tf, -INFINITY);
   const int grid = grid_for(rows * 32, 256, 1, 8);   // one warp per row until the wave is full
-  threshold_pack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, mode, d_bits, words_per_row, d_count);
+  if (mode == 0) threshold_pack_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count);
+  else threshold_pack_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
 }

@@ -186,7 +186,9 @@ def sample_ddpm_host(n_sample, diff_net, vae_net, diff_latent_dim, noise_divider
         host_out = torch.empty((n_sample, eng.I), dtype=torch.float32, pin_memory=True)
     if chunk_rows is None:
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        chunk_rows = 2 * sms * 128
+        # one CTA wave per chunk: the device->host copy of a wave (57 GB/s) is shorter than its compute, so only the LAST
+        # chunk's copy is exposed, and a one-wave chunk makes that tail as short as it gets
+        chunk_rows = int(os.environ.get("SDRM_HOST_CHUNK_WAVES", "1")) * sms * 128
     bufs = getattr(eng, "_host_bufs", None)
     if bufs is None or bufs[0].shape != (chunk_rows, eng.I):
         bufs = [torch.empty((chunk_rows, eng.I), dtype=torch.float32, device=dev) for _ in range(2)]

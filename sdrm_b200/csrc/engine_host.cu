@@ -243,8 +243,9 @@ static int max_resident_ctas(int cluster, int num_sms) {
   return n * cluster;
 }
 
-// ---- TMA tensor maps (pair mode): a blob of `rows` x 128 bytes, box = `box_rows` rows, no swizzle (the images are
-// pre-swizzled in global memory), so a box lands in shared memory byte-for-byte like the bulk copies of single mode
+// ---- TMA tensor maps: a blob of `rows` x 128 bytes, box = `box_rows` rows x `box_bytes`.  Weight maps (pair mode) take no
+// swizzle: the weight images are pre-swizzled in global memory, so a box lands in shared memory byte-for-byte like the bulk
+// copies of single mode.  The activation load map swizzles (SWIZZLE_128B), the activation store map does not.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

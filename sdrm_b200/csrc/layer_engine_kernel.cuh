@@ -3,9 +3,10 @@
 // Replaces the reference's per-step eager op chain (sample_ddpm, train_SDRM.py:50-61; SDRM.forward
 // 97-103; denoise_add_noise 20-25; VAE.decode 252-254) with ONE persistent kernel:
 //   * a CTA owns a 128-row tile of users for the whole T-step chain and the decode;
-//   * every dense layer is a tcgen05 (UMMA) GEMM: A = bf16 activations, B = bf16 weights, both
-//     stored in global memory as pre-swizzled "tile images" that one cp.async.bulk (TMA bulk engine)
-//     drops straight into the 128B-swizzled shared-memory operand layout; accumulators live in TMEM
+//   * every dense layer is a tcgen05 (UMMA) GEMM: A = bf16 activations, B = bf16 weights.  Weights are stored in global
+//     memory as pre-swizzled "tile images" that a bulk / tensor-map copy drops straight into the 128B-swizzled shared-memory
+//     operand layout; activation images are LINEAR rows in global memory (written by TMA tensor stores from the epilogue
+//     warps' shared-memory slots) and swizzled by the TMA tensor load; accumulators live in TMEM
 //     (2 x 256 columns, double-buffered so the epilogue of chunk c overlaps the UMMAs of chunk c+1);
 //   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
 //     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the

@@ -11,7 +11,7 @@
 //   * the epilogue warps fuse bias (hoisted time embedding), PReLU / tanh, the DDPM posterior update
 //     with in-kernel Philox Gaussian noise, the always-on dropout of the next step's input and the
 //     bf16 (or bf16 hi/lo) re-quantisation, and write the next layer's A images (L2-resident scratch);
-//   * warps 0-15 = epilogue, 16-19 = noise, 20 = weight TMA producer, 21 = UMMA issuer, 22 = activation TMA producer;
+//   * warps 0-11 = epilogue, 12-15 = noise, 16 = weight TMA producer, 17 = UMMA issuer, 18 = activation TMA producer;
 //     the epilogue
 //     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
 // Rows are independent, so there is no inter-CTA synchronisation anywhere.
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   static_assert((A_TILE_BYTES + W_STAGE_BYTES) % 1024 == 0, "stages stay 1024-byte aligned (SWIZZLE_128B operand atoms)");
   constexpr uint32_t STG_BYTES = A_TILE_BYTES + W_STAGE_BYTES;
   constexpr int NCTA = CS;
-  constexpr uint32_t BIAS_SLICE_BYTES = 4 * 16 * 4;   // per epilogue warp: the bias of its (at most 4) column groups of one chunk
+  constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
+  constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
   constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 2);   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // per epilogue warp: one 16-column group of its 32 rows, dense bf16 (TMA store box)
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -592,20 +593,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
         const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step;
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
-        // warp stages the 64 floats of its own groups of a chunk in a private shared-memory slice (lane l holds elements
-        // 2l, 2l+1: group slot l / 8, columns 2 (l % 8) ..) one chunk ahead, and the group loop reads them with LDS.128.
-        const int slice_g = sub + EPI_SUB * (lane >> 3);            // group whose bias this lane fetches
-        const int slice_o = slice_g * 16 + 2 * (lane & 7);
-        auto fetch_slice = [&](int c) -> float2 {
-          return (slice_g < ngroups) ? *reinterpret_cast<const float2*>(bias_row + c * NC + slice_o) : make_float2(0.f, 0.f);
+        // warp stages the 16 floats of each of its own groups of a chunk in a private shared-memory slice (lane l < 4 BIAS_SLOTS
+        // holds elements 4l .. 4l+3: group slot l / 4, columns 4 (l % 4) ..) one chunk ahead, and the group loop reads them with LDS.128.
+        const int slice_g = sub + EPI_SUB * (lane >> 2);            // group whose bias this lane fetches (lanes < 4 BIAS_SLOTS)
+        const int slice_o = slice_g * 16 + 4 * (lane & 3);
+        auto fetch_slice = [&](int c) -> float4 {
+          return (lane < 4 * BIAS_SLOTS && slice_g < ngroups) ? *reinterpret_cast<const float4*>(bias_row + c * NC + slice_o) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float2 bnext = fetch_slice(0);
+        float4 bnext = fetch_slice(0);
         for (int c = 0; c < NCH; ++c) {
           const uint32_t buf = cc & 1u;
           const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
           const int fc = c * NC;
           __syncwarp();                                             // every lane is done with the previous chunk's slice
-          *reinterpret_cast<float2*>(bias_s + 2 * lane) = bnext;
+          if (lane < 4 * BIAS_SLOTS) *reinterpret_cast<float4*>(bias_s + 4 * lane) = bnext;
           __syncwarp();
           // Software pipeline over this warp's groups: the TMEM load (and, for the posterior update, the state columns and
           // keep bits) of group g+4 is requested as soon as group g has consumed its own, so its latency hides behind the

@@ -39,6 +39,10 @@
 #ifndef SDRM_POSTERIOR_MUFU_TANH
 #define SDRM_POSTERIOR_MUFU_TANH 1   // eps = tanh.approx.f32 (1 MUFU instead of ex2 + rcp + 3 FP ops) in the posterior update
 #endif
+#ifndef SDRM_OUT_SLOTS
+#define SDRM_OUT_SLOTS 1      // shared-memory boxes per epilogue warp for the TMA activation stores; 2 = the store of a box is issued one group later
+                              // (measured r02: 278.7 / 277.4 vs 275.1 / 273.7 ms per cfg-5 shard on one box: the epilogue is not the critical path there)
+#endif
 #ifndef SDRM_STATE_CS
 #define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
 #endif
@@ -50,9 +54,17 @@
 #ifdef SDRM_PERF_DEBUG
 #define SDRM_DEBUG_SKIP_ACT_STORES (P.debug_flags & 1)
 #define SDRM_DEBUG_SKIP_NOISE (P.debug_flags & 4)
+#define SDRM_DEBUG_NOISE_NO_RNG (P.debug_flags & 16)       // state pass without Philox / Box-Muller (z = 0)
+#define SDRM_DEBUG_NOISE_NO_STATE (P.debug_flags & 32)     // Philox / Box-Muller without the state load / store
+#define SDRM_DEBUG_ACT_STORE_FIXED (P.debug_flags & 64)    // every activation box goes to row 0 of the CTA's scratch (no new dirty lines)
+#define SDRM_DEBUG_NO_STORE_WAIT (P.debug_flags & 128)     // publish chunks without waiting for the TMA stores to complete
 #else
 #define SDRM_DEBUG_SKIP_ACT_STORES 0
 #define SDRM_DEBUG_SKIP_NOISE 0
+#define SDRM_DEBUG_NOISE_NO_RNG 0
+#define SDRM_DEBUG_NOISE_NO_STATE 0
+#define SDRM_DEBUG_ACT_STORE_FIXED 0
+#define SDRM_DEBUG_NO_STORE_WAIT 0
 #endif
 
 namespace sdrm {
@@ -110,8 +122,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
   constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 2);   // mbarriers of a CTA (map below)
-  constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // per epilogue warp: one 16-column group of its 32 rows, dense bf16 (TMA store box)
-  static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
+  constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
+  constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
+  static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -426,27 +439,51 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // scattered over 32 rows this frees the source registers at once (the next iteration's loads waited for the LSU to dequeue
     // the store: 27 % of the PReLU loop's samples), needs no swizzle shuffles, and the writes stay in the async proxy, so
     // publishing a chunk is a bulk-group wait of one lane instead of a membar.gpu + proxy fence of every thread.
-    const uint32_t out_slot = out_slots + static_cast<uint32_t>(warp) * OUT_SLOT_BYTES;
+    // Two slots per warp, and the TMA store of a slot is issued one call LATER (right before the other slot is filled): by then
+    // the slot's st.shared are long complete, so the proxy fence does not wait for them, and the slot about to be overwritten
+    // was handed to the TMA a whole group iteration ago, so waiting for its read costs nothing either.  (r01f profile, PReLU
+    // group loop: 12.9 % of its samples waited for the previous box to be read, 13.2 % on the fence behind the stores.)
+    const uint32_t out_slot = out_slots + static_cast<uint32_t>(warp) * (OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES);
     const uint32_t out_lane = out_slot + static_cast<uint32_t>(lane) * 32u;
-    auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
-      // (elect.sync with a full mask always names the same lane; converged single-lane issue keeps ptxas from wrapping the
-      // uniform-datapath TMA instruction in an elect loop)
-      if (elect_one()) bulk_wait_group_read<0>();   // the previous box has been read out of the slot
-      __syncwarp();
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
-      fence_proxy_async_smem();
-      __syncwarp();
-      // first row of the box = row 32 q of the tile (lane 0's buf_row)
-      const int y = __shfl_sync(0xffffffffu, static_cast<int>((buf_row - P.scratch) >> 7), 0) + (f0 >> 6) * TILE_M;
-      if (elect_one()) {
-        tma_store_2d_hint(&P.tm_act_st, (f0 & 63) * 2, y, out_slot, pol_keep);
-        bulk_commit_group();
+    uint32_t slot_sel = 0;     // slot written last
+    int pend_x = -1, pend_y = 0;   // tensor coordinates of the box waiting in slot `slot_sel` (pend_x < 0: none)
+    auto flush_pending = [&]() {
+      if (pend_x >= 0) {   // warp-uniform
+        fence_proxy_async_smem();
+        __syncwarp();
+        // (elect.sync with a full mask always names the same lane; converged single-lane issue keeps ptxas from wrapping the
+        // uniform-datapath TMA instruction in an elect loop)
+        if (elect_one()) {
+          tma_store_2d_hint(&P.tm_act_st, pend_x, pend_y, out_slot + slot_sel * OUT_SLOT_BYTES, pol_keep);
+          bulk_commit_group();
+        }
+        pend_x = -1;
       }
+    };
+    auto store_act = [&](uint8_t* buf_row, int f0, const uint32_t (&pk)[8]) {
+      flush_pending();
+      if (OUT_SLOTS_PER_WARP == 1) {
+        if (elect_one()) bulk_wait_group_read<0>();   // the box has been read out of the slot
+      } else {
+        if (elect_one()) bulk_wait_group_read<1>();   // every box but the one just issued has been read: the other slot is free
+        slot_sel ^= 1u;
+      }
+      __syncwarp();
+      const uint32_t dst = out_lane + slot_sel * OUT_SLOT_BYTES;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + 16u), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+      // first row of the box = row 32 q of the tile (lane 0's buf_row)
+      pend_y = __shfl_sync(0xffffffffu, static_cast<int>((buf_row - P.scratch) >> 7), 0) + (f0 >> 6) * TILE_M;
+      if (SDRM_DEBUG_ACT_STORE_FIXED) pend_y = static_cast<int>((static_cast<size_t>(blockIdx.x) * P.scratch_stride) >> 7) + 32 * q;
+      pend_x = (f0 & 63) * 2;
+      if (OUT_SLOTS_PER_WARP == 1) flush_pending();
     };
     // all TMA stores of this warp have been written (lane 0 issued them): what a chunk / tile publication waits for
     auto stores_done = [&]() {
-      if (elect_one()) bulk_wait_group<0>();
+      flush_pending();
+      if (!SDRM_DEBUG_NO_STORE_WAIT) {
+        if (elect_one()) bulk_wait_group<0>();
+      }
       __syncwarp();
     };
     // dropout (F.dropout p = .5: kept values are doubled) + bf16 pack of 16 state values
@@ -805,6 +842,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int l = 0; l < P.n_dec; ++l)
         for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s);
     }
+    stores_done();   // no TMA store may still be reading this CTA's shared memory at exit
   } else {
     // ======================================= noise warps ========================================
     // Thread r owns tile row r.  For every step i it (1) writes the dropout keep bits of step i-1 (one Philox call per 128
@@ -872,13 +910,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           auto half_group = [&](int g16, int hf, bool padded) {
             float xo[8];
             float* px = xstate_ptr8(xs, g16, hf, r);
+            if (SDRM_DEBUG_NOISE_NO_STATE) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) xo[e] = 0.5f;
+            } else
             asm volatile("ld.global" SDRM_ST_HINT ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                          : "=f"(xo[0]), "=f"(xo[1]), "=f"(xo[2]), "=f"(xo[3]), "=f"(xo[4]), "=f"(xo[5]), "=f"(xo[6]), "=f"(xo[7])
                          : "l"(px)
                          : "memory");
             float z[8];
             const int f0 = g16 * 16 + hf * 8;
-            if (has_z) {
+            if (has_z && !SDRM_DEBUG_NOISE_NO_RNG) {
               if (P.inj_z) {
                 const float* zp = P.inj_z + (static_cast<size_t>(i) * P.n_rows + row) * L;
 #pragma unroll
@@ -906,6 +948,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               for (int e = 0; e < 8; ++e)
                 if (f0 + e >= L) xo[e] = 0.0f;   // padding columns stay exactly 0
             }
+            if (SDRM_DEBUG_NOISE_NO_STATE) {
+              float acc = 0.f;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc += xo[e];
+              if (acc == 12345.678f) px[0] = acc;   // keeps the arithmetic alive
+            } else
             asm volatile("st.global" SDRM_ST_HINT ".v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                          ::"l"(px), "f"(xo[0]), "f"(xo[1]), "f"(xo[2]), "f"(xo[3]), "f"(xo[4]), "f"(xo[5]), "f"(xo[6]), "f"(xo[7])
                          : "memory");

@@ -4,7 +4,8 @@ Per minibatch of latents mu = VAE.encode(x):
   1. K2 `sdrm_noise_inputs`  : noise, x_t = sqrt(ab_t) mu + (1-ab_t) noise, x_p = mu + .1 noise and the three
                                dropout-scaled denoiser inputs, one fused pass (in-kernel Philox);
   2. the three denoiser forwards run as ONE [3B, L] batch through the shared MLP (rows are independent, so
-     this is the same arithmetic; the dense layers are library GEMMs under autograd);
+     this is the same arithmetic); every dense product of the forward AND the backward runs on the hand-written
+     tcgen05 GEMM (`DenoiserGemms` -> C ABI `sdrm_denoiser_fwd/bwd`, bf16x3 split operands, fp32 accumulate);
   3. K2 `sdrm_loss_stats` + `sdrm_loss_grad_seeds`: five fp64 partial sums -> (optional all-reduce over the
      data-parallel group: the loss divides by the GLOBAL-batch variance) -> scalar loss and
      the closed-form gradient seeds, wrapped in a torch.autograd.Function.
@@ -135,6 +136,81 @@ class FrozenEncoder:
         return torch.addmm(self.b2mu, self.hidden(x), self.W2mu)
 
 
+class DenoiserGemms(torch.autograd.Function):
+    """eps_theta for the batched [3B, L] rows with every dense product on the hand-written tcgen05 GEMM
+    (C ABI `sdrm_denoiser_fwd` / `sdrm_denoiser_bwd`, csrc/train_gemm.cu).  Reference: SDRM.forward (train_SDRM.py:97-103)
+    called three times by score_matching_loss (191-199) and differentiated by autograd (336).
+
+    The time embedding enters as a hoisted table (table[i] = W0[:, L:] (We temb(i) + be) + b0, built by the caller in torch
+    so that autograd carries d table back to We, be, W0[:, L:] and b0): layer 0 is a K = L product plus a gathered bias row.
+    """
+
+    @staticmethod
+    def forward(ctx, x, t, table, W0, a0, Wh, bh, ah, Wo, bo, L, nh, passes):
+        lib = _lib.load()
+        if x.device.type != "cuda":
+            raise _lib.SdrmError("DenoiserGemms: CUDA tensors required (no CPU fallback)")
+        x = x.detach().contiguous().float()
+        t = t.detach().to(torch.int64).contiguous()
+        rows, D = x.shape[0], W0.shape[0]
+        tens = [v.detach() if v is not None else None for v in (table, W0, a0, Wh, bh, ah, Wo, bo)]
+        table_, W0_, a0_, Wh_, bh_, ah_, Wo_, bo_ = [v.contiguous().float() if v is not None else None for v in tens]
+        need = lib.sdrm_denoiser_train_workspace_bytes(rows, L, D, nh)
+        if need == 0:
+            raise _lib.SdrmError("sdrm_denoiser_train_workspace_bytes failed: " + lib.sdrm_last_error().decode())
+        ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        out = torch.empty((rows, L), dtype=torch.float32, device=x.device)
+        st = _lib.stream_ptr()
+        rc = lib.sdrm_denoiser_fwd(_lib.ptr(x), _lib.ptr(t), _lib.ptr(table_), table_.stride(0), _lib.ptr(W0_), W0_.stride(0),
+                                   _lib.ptr(a0_), _lib.ptr(Wh_), _lib.ptr(bh_), _lib.ptr(ah_), _lib.ptr(Wo_), _lib.ptr(bo_),
+                                   rows, L, D, nh, passes, _lib.ptr(out), _lib.ptr(ws), need, st)
+        _lib.check(rc, "sdrm_denoiser_fwd")
+        ctx.save_for_backward(x, t, out, a0_, Wh_, ah_, Wo_, ws)
+        ctx.dims = (rows, L, D, nh, passes, table_.shape[0] - 1, W0.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        x, t, out, a0, Wh, ah, Wo, ws = ctx.saved_tensors
+        rows, L, D, nh, passes, T, w0_cols = ctx.dims
+        g_out = g_out.detach().contiguous().float()
+        order = torch.argsort(t, stable=True).contiguous()
+        offsets = torch.zeros(T + 2, dtype=torch.int64, device=t.device)
+        offsets[1:] = torch.cumsum(torch.bincount(t, minlength=T + 1), 0)
+        dev = x.device
+        gW0 = torch.empty((D, L), dtype=torch.float32, device=dev)
+        gTable = torch.empty((T + 1, D), dtype=torch.float32, device=dev)
+        ga0 = torch.empty(1, dtype=torch.float32, device=dev)
+        gWo = torch.empty((L, D), dtype=torch.float32, device=dev)
+        gbo = torch.empty(L, dtype=torch.float32, device=dev)
+        gWh = gbh = gah = None
+        if nh > 0:
+            gWh = torch.empty((D, D), dtype=torch.float32, device=dev)
+            gbh = torch.empty(D, dtype=torch.float32, device=dev)
+            gah = torch.empty(1, dtype=torch.float32, device=dev)
+        rc = lib.sdrm_denoiser_bwd(_lib.ptr(g_out), _lib.ptr(out), _lib.ptr(x), _lib.ptr(order), _lib.ptr(offsets), T, _lib.ptr(a0),
+                                   _lib.ptr(Wh), _lib.ptr(ah), _lib.ptr(Wo), rows, L, D, nh, passes, _lib.ptr(gW0), _lib.ptr(gTable),
+                                   _lib.ptr(ga0), _lib.ptr(gWh), _lib.ptr(gbh), _lib.ptr(gah), _lib.ptr(gWo), _lib.ptr(gbo),
+                                   _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "sdrm_denoiser_bwd")
+        gW0_full = torch.zeros((D, w0_cols), dtype=torch.float32, device=dev)
+        gW0_full[:, :L] = gW0
+        return None, None, gTable, gW0_full, ga0, gWh, gbh, gah, gWo, gbo, None, None, None
+
+
+def denoiser_gemms(net, x, t, passes=3):
+    """SDRM.forward(x, t, prescaled=True) with the Linear layers on the tcgen05 GEMM; differentiable wrt net's parameters."""
+    lt = net.layer_tensors()
+    T = net.EMB_DIM
+    L = lt["W0"].shape[1] - T
+    steps = torch.arange(T + 1, device=x.device)
+    emb = net.emb_layer(net.timestep_embedding(steps, T))                       # [T+1, T]   (tiny: stays in torch / autograd)
+    table = torch.nn.functional.linear(emb, lt["W0"][:, L:], lt["b0"])         # [T+1, D]
+    return DenoiserGemms.apply(x, t, table, lt["W0"], lt["a0"], lt["Wh"], lt["bh"], lt["ah"], lt["Wo"], lt["bo"],
+                               L, net.n_hidden_layers, int(passes))
+
+
 class ScoreMatchingLoss(torch.autograd.Function):
     """loss = 0.5 (mean((sd-r)^2) + mean((r-sx)^2)) / (1e-8 + var(r)),  r = pred - mu, sd = (psx - sx)/mu_coef^2,
     with means / variance over the GLOBAL batch when `group` is a process group."""
@@ -159,8 +235,11 @@ class ScoreMatchingLoss(torch.autograd.Function):
 class DiffusionTrainStep:
     """Builds the loss of one minibatch; the caller does zero_grad / backward / optimizer.step like the reference."""
 
-    def __init__(self, diff_net, ab_t, timesteps, noise_divider, mu_coef=0.1, group=None, backend=None, seed=None):
+    def __init__(self, diff_net, ab_t, timesteps, noise_divider, mu_coef=0.1, group=None, backend=None, seed=None, gemm_passes=3):
         self.net = diff_net
+        # dense layers: 3 = bf16x3 products on the tcgen05 GEMM (fp32-grade), 1 = plain bf16 operands, 0 = torch / cuBLAS
+        # (kept for comparison runs and for the CPU test backend)
+        self.gemm_passes = int(gemm_passes)
         self.ab_t = ab_t.detach().to(torch.float32).contiguous()
         self.T = int(timesteps)
         self.nd = float(noise_divider)
@@ -185,6 +264,9 @@ class DiffusionTrainStep:
         _, in_pert, in_clean, in_shift, _ = self.backend.noise_inputs(
             mu, t, self.ab_t.to(mu.device), self.nd, self.mu_coef, seed, self.row_offset, inj_noise, inj_masks)
         x3 = torch.cat([in_pert, in_clean, in_shift], dim=0)
-        out3 = self.net(x3, t.repeat(3), prescaled=True)
+        if self.gemm_passes and isinstance(self.backend, CudaLossBackend):
+            out3 = denoiser_gemms(self.net, x3, t.repeat(3), self.gemm_passes)
+        else:
+            out3 = self.net(x3, t.repeat(3), prescaled=True)
         pred, sx, psx = out3[:B], out3[B:2 * B], out3[2 * B:]
         return ScoreMatchingLoss.apply(pred, sx, psx, mu, self.mu_coef, self.backend, self.group)

@@ -9,8 +9,10 @@ configuration BASELINE.json quotes its target on: the synthetic scale-up (T=178,
 `value`   : device-timed, output stays in HBM.
 `e2e`     : through the public API with the rows delivered into pinned HOST memory (D2H inside the timed region).
 `roofline`: tensor-pipe fraction of the persistent kernel vs the measured sustained bf16 peak.
-`cpu_baseline`: the oracle (CPU restatement of the reference, incl. its RNG draws) on the box's host cores.
-`--impl reference` times that CPU implementation alone with all host threads (rank 0 only).
+`cpu_baseline`: the reference's own sample_ddpm (unmodified files under the git-ignored baseline/_ref/, staged by build()) on
+               the box's host cores; the oracle port only if the reference is not on the box.
+`--impl reference` times that CPU implementation alone with all host threads (rank 0 only) and adds `eager_cuda`: the same
+               reference code with DEVICE='cuda' (PyTorch eager) on this box's GPU.
 """
 import argparse
 import json
@@ -101,9 +103,58 @@ def build_models(w, device, seed=0):
     return diff, vae
 
 
-def cpu_reference_rate(w, rows, threads, repeats=1):
-    """users/s of the CPU restatement of sample_ddpm (oracle), RNG draws inside the timed region like the reference."""
+def _reference_module():
+    """The reference's OWN train_SDRM module (unmodified files staged under the git-ignored baseline/_ref/ by build(), imported
+    through oracle/refstub.py's optuna / bottleneck stubs), or None when it is not available on this box."""
+    try:
+        from oracle import refstub
+        if not refstub.reference_available():
+            return None
+        return refstub.import_reference()
+    except Exception as exc:   # fall back to the oracle port
+        sys.stderr.write(f"reference import failed ({exc!r}); timing the oracle port instead\n")
+        return None
+
+
+def reference_rate(w, rows, device, threads=None, repeats=1):
+    """users/s of the reference's own sample_ddpm (train_SDRM.py:27-63, full mode) on `device` ('cpu' or 'cuda'): its module
+    global DEVICE and schedule globals are set the way its train_SDRM() sets them (297-303); models are the reference's own
+    classes, random-init (timing is weight-independent)."""
     import torch
+    from oracle import sdrm_oracle as orc
+    ref = _reference_module()
+    if ref is None:
+        return None
+    if threads:
+        torch.set_num_threads(threads)
+    ref.DEVICE = device
+    b_t, a_t, ab_t = orc.make_schedule(w["T"])
+    ref.b_t, ref.a_t, ref.ab_t = b_t.to(device), a_t.to(device), ab_t.to(device)
+    torch.manual_seed(0)
+    vae = ref.VAE(input_dim=w["I"], hidden_dim=w["H"], latent_dim=w["L"]).to(device).eval()
+    diff = ref.SDRM(N_ITEMS=w["L"], EMB_DIM=w["T"], LATENT_DIM=w["L"], n_hidden_layers=w["nh"]).to(device).eval()
+    best = None
+    for _ in range(repeats):
+        if device != "cpu":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = ref.sample_ddpm(rows, diff, vae, w["L"], w["nd"], n_timesteps=w["T"])
+        if device != "cpu":
+            torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    assert tuple(out.shape) == (rows, w["I"])
+    del out
+    return rows / best, best
+
+
+def cpu_reference_rate(w, rows, threads, repeats=1):
+    """(users/s, seconds, kind): the reference's own sample_ddpm on the host cores when it is staged on this box (kind
+    'reference'), else the CPU restatement (oracle, kind 'port'); RNG draws inside the timed region like the reference."""
+    import torch
+    r = reference_rate(w, rows, "cpu", threads, repeats)
+    if r is not None:
+        return r[0], r[1], "reference"
     from oracle import sdrm_oracle as orc
     torch.set_num_threads(threads)
     diff, vae = build_models(w, "cpu")
@@ -125,21 +176,39 @@ def cpu_reference_rate(w, rows, threads, repeats=1):
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
     assert out.shape == (rows, w["I"])
-    return rows / best, best
+    return rows / best, best, "port"
+
+
+def _cpu_sample_text(kind, rows, w):
+    src = "the reference's own train_SDRM.sample_ddpm (baseline/_ref, unmodified)" if kind == "reference" else "oracle/sdrm_oracle.py (port)"
+    return f"{rows} users x full T={w['T']} chain + decode per step, {src}, torch CPU, RNG draws inside the timed region"
 
 
 def run_reference(args, w, rank):
     if rank != 0:
         return
+    import torch
     threads = os.cpu_count() or 1
     rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / flops_per_user(w))))
     for _ in range(args.warmup):
         cpu_reference_rate(w, max(8, rows // 8), threads)
-    t_all = 0.0
+    t_all, kind = 0.0, "port"
     for _ in range(args.steps):
-        rate, dt = cpu_reference_rate(w, rows, threads)
+        rate, dt, kind = cpu_reference_rate(w, rows, threads)
         t_all += dt
     value = rows * args.steps / t_all
+    # second stated baseline: the SAME reference code with DEVICE='cuda' -- PyTorch eager / cuBLAS fp32
+    # on this box's GPU 0, a bounded sample of the workload
+    eager = None
+    if torch.cuda.is_available() and _reference_module() is not None and not args.no_eager:
+        try:
+            erows = args.eager_rows or min(w["n"], 32768)
+            reference_rate(w, max(128, erows // 8), "cuda")
+            r = reference_rate(w, erows, "cuda", repeats=2)
+            eager = {"value": r[0], "unit": "users/s", "rows_per_step": erows, "seconds": r[1],
+                     "what": "reference train_SDRM.sample_ddpm unmodified, DEVICE='cuda' (PyTorch eager, fp32 cuBLAS), GPU 0, output left on the device"}
+        except Exception as exc:
+            eager = {"error": repr(exc)[:200]}
     line = {
         "impl": "reference", "metric": "synthetic users/sec (full reverse diffusion + decode)", "value": value,
         "unit": "users/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -147,9 +216,9 @@ def run_reference(args, w, rank):
         "dtype": "f32", "data": "synthetic (random-init weights of the named shape, torch CPU RNG)",
         "config": {"workload": args.workload, **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
                    "rows_per_step": rows, "note": "bounded sample of the workload on host cores"},
-        "cpu_baseline": {"value": value, "unit": "users/s", "cores": threads, "kind": "port",
-                         "sample": f"{rows} users x full T={w['T']} chain + decode per step, oracle/sdrm_oracle.py"},
+        "cpu_baseline": {"value": value, "unit": "users/s", "cores": threads, "kind": kind, "sample": _cpu_sample_text(kind, rows, w)},
         "e2e": {"value": value, "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "eager_cuda": eager,
     }
     emit(line)
 
@@ -177,12 +246,14 @@ def run_ours(args, w, rank, world, local_rank):
         torch.cuda.synchronize(dev)
 
     from sdrm_b200 import _lib as _l
-    _l.load().sdrm_set_cluster_override(args.cluster)
-    _l.load().sdrm_set_subtile_override(args.subtiles)
-    _l.load().sdrm_debug_set_flags(int(os.environ.get("SDRM_DEBUG_FLAGS", "0")))
+    eng = engine_for(diff, dev)
+    eng.set_option(_l.OPT_CLUSTER, args.cluster)
+    eng.set_option(_l.OPT_SUBTILES, args.subtiles)
+    eng.set_option(_l.OPT_NO_DISCARD, int(os.environ.get("SDRM_NO_DISCARD", "0")))   # A/B of the dead-buffer discard
+    if int(os.environ.get("SDRM_DEBUG_FLAGS", "0")):    # perf experiments (tools/ablate.sh): -DSDRM_PERF_DEBUG builds only
+        eng.set_option(_l.OPT_DEBUG_FLAGS, int(os.environ["SDRM_DEBUG_FLAGS"]))
     for i in range(args.warmup):
         step(1000 + i)
-    eng = engine_for(diff, dev)
     barrier()
     from sdrm_b200 import _lib
     _lib.check(eng.lib.sdrm_check_device_error(eng.handle, _lib.stream_ptr()), "warmup")
@@ -289,9 +360,8 @@ def run_ours(args, w, rank, world, local_rank):
         if not args.no_cpu and world == 1:   # reported on rank 0 at N=1 only
             threads = os.cpu_count() or 1
             rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / F)))
-            rate, dt = cpu_reference_rate(w, rows, threads)
-            cpu = {"value": rate, "unit": "users/s", "cores": threads, "kind": "port",
-                   "sample": f"{rows} users x full T={w['T']} chain + decode, {dt:.1f} s, oracle/sdrm_oracle.py incl. RNG draws"}
+            rate, dt, kind = cpu_reference_rate(w, rows, threads)
+            cpu = {"value": rate, "unit": "users/s", "cores": threads, "kind": kind, "seconds": dt, "sample": _cpu_sample_text(kind, rows, w)}
         line = {
             "metric": "synthetic users/sec (full reverse diffusion + decode)", "value": value, "unit": "users/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -303,6 +373,116 @@ def run_ours(args, w, rank, world, local_rank):
                        "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
             "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "subtiles": args.subtiles, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
+        }
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+
+def train_flops_per_row(w):
+    """Algorithmic FLOPs of one diffusion training step per minibatch row (train_SDRM.py:331-337): three denoiser forwards,
+    their weight gradients, and the data gradients of every layer but the first (nothing upstream of layer 0 needs one);
+    the hoisted time-embedding table (two [T+1, T] products) is not counted; bf16x3 products are credited once."""
+    L, nh = w["L"], w["nh"]
+    return 3 * 2 * L * L * ((2 + nh) + (2 + nh) + (1 + nh))
+
+
+def run_train(args, w, rank, world, local_rank):
+    """`--mode train`: one diffusion training step (fused noising, 3 forwards, score-matching loss, backward, Adam) per
+    minibatch of B latent rows per GPU at the workload's layer shape; data-parallel over `world` GPUs exactly like
+    sdrm_b200.distributed.dp_train_step (5-scalar statistics all-reduce + flat gradient all-reduce over NCCL)."""
+    import torch
+    import torch.distributed as dist
+    from sdrm_b200 import distributed as sd
+    from sdrm_b200.models import make_schedule
+    from sdrm_b200.training import DiffusionTrainStep
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.rows or args.train_batch
+    diff, _ = build_models(dict(w, I=64, H=64), dev)     # the VAE is not part of the step (mu is an input)
+    diff.train()
+    _, _, ab_t = make_schedule(w["T"], device=dev)
+    group = dist.group.WORLD if world > 1 else None
+
+    def make(passes):
+        st = DiffusionTrainStep(diff, ab_t, w["T"], w["nd"], group=group, seed=77, gemm_passes=passes)
+        st.row_offset = rank * B
+        opt = torch.optim.Adam(diff.parameters(), lr=1e-5, weight_decay=1e-4, eps=1e-8)
+        return st, opt
+
+    torch.manual_seed(1 + rank)
+    mu_host = torch.randn(B, w["L"]).pin_memory()
+    mu = mu_host.to(dev)
+
+    def step(st, opt, src):
+        opt.zero_grad(set_to_none=False)
+        loss = st.loss(src if src.is_cuda else src.to(dev, non_blocking=True))
+        loss.backward()
+        sd.allreduce_gradients(diff, group)
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(passes, steps, src):
+        st, opt = make(passes)
+        for _ in range(args.warmup):
+            step(st, opt, src)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            loss = step(st, opt, src)
+        e1.record()
+        if not src.is_cuda:
+            float(loss.item())     # e2e: the loss scalar comes back to the host (train_SDRM.py:335)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1), wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0].item()), float(ms[1].item()), float(loss.item())
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms3, _, loss3 = timed(3, args.steps, mu)
+    clock_info = clocks.stop() if rank == 0 else None
+    ms1, _, _ = timed(1, args.steps, mu)
+    ms0, _, loss0 = timed(0, args.steps, mu)
+    _, wall_e2e, _ = timed(3, max(args.e2e_steps, 5), mu_host)
+    e2e_steps = max(args.e2e_steps, 5)
+    if rank == 0:
+        peaks = measured_peaks()
+        F = train_flops_per_row(w) * B
+        rows_s = world * B * args.steps / (ms3 * 1e-3)
+        ach = F * args.steps / (ms3 * 1e-3) / 1e12
+        line = {
+            "metric": "diffusion training rows/sec (noising + 3 forwards + loss + backward + Adam)", "value": rows_s, "unit": "rows/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms3 / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3 (fp32-grade split products), fp32 accumulate",
+            "data": "synthetic (random-init denoiser of the named shape, N(0,1) latents, in-kernel Philox noise / t)",
+            "config": {"workload": args.workload + "-train", "rows_per_gpu": B, **{k: w[k] for k in ("L", "T", "nh", "nd")},
+                       "l2": "every step streams > 1 GB of activations (rows x L x 4 B per layer, >> 126 MB L2)"},
+            "clocks": clock_info,
+            "e2e": {"value": world * B * e2e_steps / (wall_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": B * w["L"] * 4,
+                    "d2h_bytes_per_step": 4, "steps": e2e_steps,
+                    "note": "latent minibatch uploaded from pinned host memory every step, loss scalar read back; wall clock"},
+            "gpu_launches": None,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                         "traffic": None, "kernel": "sdrm_gemm_pair_kernel (bf16x3: executes 3x the credited products)",
+                         "flops_per_row": train_flops_per_row(w), "peak_source": peaks["source"] + " sustained bf16"},
+            "variants": {"bf16x3_ms_per_step": ms3 / args.steps, "bf16_single_pass_ms_per_step": ms1 / args.steps,
+                         "torch_cublas_fp32_ms_per_step": ms0 / args.steps, "loss_bf16x3": loss3, "loss_torch": loss0},
+            "cpu_baseline": None,
         }
         emit(line)
     if world > 1:
@@ -332,12 +512,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--mode", choices=["sample", "train"], default="sample", help="train: one diffusion training step per minibatch")
+    ap.add_argument("--train-batch", type=int, default=16384, help="--mode train: minibatch rows per GPU")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="cfg5")
     ap.add_argument("--rows", type=int, default=None, help="override users per GPU")
     ap.add_argument("--cpu-rows", type=int, default=None, help="rows of the CPU baseline sample")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="--impl reference: skip the eager-CUDA run of the reference")
+    ap.add_argument("--eager-rows", type=int, default=None, help="--impl reference: rows of the eager-CUDA sample")
     ap.add_argument("--cluster", type=int, default=0, help="force the weight-multicast cluster size (1, 2, 4); 0 = auto")
     ap.add_argument("--subtiles", type=int, default=0, help="row tiles a CTA pair interleaves (1, 2); 0 = auto")
     args = ap.parse_args()
@@ -351,6 +535,9 @@ def main():
         return
     if world != args.gpus and args.gpus > 1:
         raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    if args.mode == "train":
+        run_train(args, w, rank, world, local_rank)
+        return
     run_ours(args, w, rank, world, local_rank)
 
 

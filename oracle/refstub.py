@@ -12,7 +12,34 @@ import os
 import sys
 import types
 
-REFERENCE_DIR = os.environ.get("SDRM_REFERENCE_DIR", "/root/reference")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_DIR = os.path.join(_ROOT, "baseline", "_ref")   # git-ignored copy that travels to the GPU box (stage_reference)
+_FILES = ("train_SDRM.py", "utilities.py", "dataloaders.py", "svd_benchmark.py", "main.py", "hyperparameter_search.py",
+          "mlp_benchmark.py", "neural_cf_benchmark_pt.py")
+
+
+def _pick_dir():
+    env = os.environ.get("SDRM_REFERENCE_DIR")
+    for d in (env, "/root/reference", STAGED_DIR):
+        if d and os.path.isfile(os.path.join(d, "train_SDRM.py")):
+            return d
+    return env or "/root/reference"
+
+
+REFERENCE_DIR = _pick_dir()
+
+
+def stage_reference(src="/root/reference"):
+    """Copy the reference's (unmodified) Python files into the git-ignored baseline/_ref/ so that `bench.py --impl reference`
+    can time the reference's OWN sample_ddpm on the GPU box, where /root/reference does not exist.  Never tracked by git."""
+    import shutil
+    if not os.path.isfile(os.path.join(src, "train_SDRM.py")):
+        return False
+    os.makedirs(STAGED_DIR, exist_ok=True)
+    for f in _FILES:
+        if os.path.isfile(os.path.join(src, f)):
+            shutil.copyfile(os.path.join(src, f), os.path.join(STAGED_DIR, f))
+    return True
 
 
 def reference_available():

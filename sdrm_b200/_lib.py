@@ -25,12 +25,7 @@ SIGNATURES = {
     "sdrm_last_launch_count": (C.c_int, [_P]),
     "sdrm_check_device_error": (C.c_int, [_P, _P]),
     "sdrm_probe_linear_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
-    "sdrm_probe_set_repeat": (None, [C.c_int]),
-    "sdrm_set_cluster_override": (None, [C.c_int]),
-    "sdrm_set_subtile_override": (None, [C.c_int]),
-    "sdrm_debug_set_grid_limit": (None, [C.c_int]),
-    "sdrm_debug_set_trace": (None, [_P]),
-    "sdrm_debug_set_flags": (None, [C.c_int]),
+    "sdrm_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "sdrm_last_cluster_size": (C.c_int, [_P]),
     "sdrm_resident_ctas": (C.c_int, [_P, C.c_int]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
@@ -56,6 +51,9 @@ SIGNATURES = {
                                C.c_size_t, _P]),
     "sdrm_loss_grad_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, _P, _P, _P, _P, _P, _P]),
 }
+
+
+OPT_CLUSTER, OPT_SUBTILES, OPT_GRID_LIMIT, OPT_NO_DISCARD, OPT_DEBUG_FLAGS, OPT_TRACE_BUFFER = 1, 2, 3, 4, 100, 101   # enum sdrm_option
 
 
 class SdrmError(RuntimeError):

@@ -175,7 +175,15 @@ struct sdrm_handle {
   int last_launches = 0;
   int last_cluster = 1;
   int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // resident CTAs per cluster size (1, 2, 4, 8)
-  int* err_word = nullptr;
+  int* err_word = nullptr;        // device view of the watchdog word
+  volatile int* err_host = nullptr;   // host view: the word lives in mapped pinned host memory, so it survives a device trap
+  // per-handle tuning options (sdrm_set_option); 0 = automatic
+  int cluster_override = 0;     // 1 / 2 / 4 / 8
+  int subtile_override = 0;     // 1 / 2 row tiles a CTA interleaves
+  int no_discard = 0;           // 1 = keep dead activation lines in the L2 (A/B of the discard warp)
+  int grid_limit = 0;           // cap on the CTAs of an sdrm_sample launch (tests: small inputs exercise the multi-tile loops)
+  int debug_flags = 0;          // -DSDRM_PERF_DEBUG builds only
+  unsigned long long* trace = nullptr;   // -DSDRM_TRACE builds only
   // denoiser
   bool have_den = false;
   int T = 0, L = 0, D = 0, nh = 0;
@@ -204,12 +212,6 @@ static void free_dec(sdrm_handle* h) {
   h->b1 = h->b2 = nullptr;
   h->have_dec = false;
 }
-
-static int g_cluster_override = 0;  // 0 = automatic
-static int g_subtile_override = 0;  // 0 = automatic, 1 / 2 = row tiles a CTA interleaves
-static int g_grid_limit = 0;        // test hook: cap on the CTAs of an sdrm_sample launch (0 = none)
-static int g_debug_flags = 0;
-static unsigned long long* g_trace = nullptr;  // debug timeline buffer (device), see sdrm_debug_set_trace
 
 static int engine_set_smem_attr() {
   static bool done[64] = {false};
@@ -349,8 +351,17 @@ int sdrm_create(sdrm_handle** out, int device) {
   sdrm_handle* h = new sdrm_handle();
   h->device = device;
   h->num_sms = prop.multiProcessorCount;
-  SDRM_CUDA(cudaMalloc(&h->err_word, sizeof(int)));
-  SDRM_CUDA(cudaMemset(h->err_word, 0, sizeof(int)));
+  {
+    // the watchdog word is zero-copy host memory: a trapped kernel leaves the context unusable, but the role code it wrote
+    // can still be read and reported (sdrm_check_device_error)
+    void* hp = nullptr;
+    SDRM_CUDA(cudaHostAlloc(&hp, 8 * sizeof(int), cudaHostAllocMapped));
+    memset(hp, 0, 8 * sizeof(int));
+    void* dp = nullptr;
+    SDRM_CUDA(cudaHostGetDevicePointer(&dp, hp, 0));
+    h->err_host = static_cast<volatile int*>(hp);
+    h->err_word = static_cast<int*>(dp);
+  }
   if (engine_set_smem_attr() != SDRM_OK) { delete h; return SDRM_ERR_CUDA; }
   h->resident[1] = h->num_sms;
   h->resident[2] = max_resident_ctas(2, h->num_sms);
@@ -365,7 +376,7 @@ int sdrm_destroy(sdrm_handle* h) {
   cudaSetDevice(h->device);
   free_den(h);
   free_dec(h);
-  cudaFree(h->err_word);
+  if (h->err_host) cudaFreeHost(const_cast<int*>(h->err_host));
   delete h;
   return SDRM_OK;
 }
@@ -530,22 +541,22 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.mask_off = mask_off;
   P.mask_pitch = mask_pitch;
   P.err_word = h->err_word;
-  P.trace = g_trace;
-  P.debug_flags = g_debug_flags;
+  P.trace = h->trace;
+  P.debug_flags = h->debug_flags;
   // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
   // full-resolution chains run on tcgen05 cta_group::2 CTA pairs (fewer weight bytes and more k-blocks in flight per SM);
   // multi-resolution chains (per-tile step counts) and single-tile calls use single-CTA mode
   if (d_t_start == nullptr && n_tiles >= 2) cluster = 2;
-  if (g_cluster_override > 0 && (d_t_start == nullptr || g_cluster_override == 1)) cluster = g_cluster_override;
+  if (h->cluster_override > 0 && (d_t_start == nullptr || h->cluster_override == 1)) cluster = h->cluster_override;
   int launch_grid = 0;
   for (; cluster >= 1; cluster >>= 1) {
     const int resident = h->resident[cluster];
     if (resident <= 0) continue;
     const long long want = (n_tiles + cluster - 1) / cluster * cluster;
     launch_grid = static_cast<int>(std::min<long long>(want, resident));
-    if (g_grid_limit > 0) launch_grid = std::min(launch_grid, std::max(cluster, g_grid_limit / cluster * cluster));
+    if (h->grid_limit > 0) launch_grid = std::min(launch_grid, std::max(cluster, h->grid_limit / cluster * cluster));
     break;
   }
   if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
@@ -562,7 +573,16 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // 67 %, DRAM traffic grows by half and the shard takes 309.6 instead of 295.6 ms; so the default stays one tile and the
   // interleave is an opt-in for shapes whose scratch fits the L2)
   P.n_sub = 1;
-  if (g_subtile_override == 2 && cluster >= 2 && n_local >= 2) P.n_sub = 2;
+  if (h->subtile_override == 2 && cluster >= 2 && n_local >= 2) P.n_sub = 2;
+  // Dead-buffer discard (pair mode, see the kernel's discard warp): whole k-blocks of a chain layer's input image that EVERY
+  // chain layer's epilogue rewrites completely (64-column blocks below the narrowest written width), so a partly written
+  // last k-block keeps the zero padding it got at kernel start.
+  P.discard_kb = 0;
+  if (cluster >= 2 && !h->no_discard && h->T >= 2) {
+    const int written = std::min(std::min(h->g0.Np, h->nh > 0 ? h->gh.Np : h->g0.Np), std::min(h->go.Np, P.Lg16 * 16));
+    const int kb_read = std::min(std::min(h->g0.KB, h->nh > 0 ? h->gh.KB : h->g0.KB), h->go.KB);
+    P.discard_kb = std::max(0, std::min(written / KBLK, kb_read));
+  }
   if (static_cast<size_t>(launch_grid) * P.n_sub * stride > workspace_bytes)
     return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small for the sub-tile scratch slots");
   rc = launch_engine(P, launch_grid, cluster, st);
@@ -576,12 +596,12 @@ int sdrm_last_launch_count(const sdrm_handle* h) { return h ? h->last_launches :
 int sdrm_check_device_error(sdrm_handle* h, void* stream) {
   if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "null handle");
   cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
-  int word = 0;
-  cudaError_t e2 = cudaMemcpy(&word, h->err_word, sizeof(int), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess || e2 != cudaSuccess || word != 0) {
+  const int word = h->err_host ? *h->err_host : 0;
+  if (e != cudaSuccess || word != 0) {
     char msg[200];
-    snprintf(msg, sizeof msg, "device error: sync=%s copy=%s watchdog=%d", cudaGetErrorString(e),
-             cudaGetErrorString(e2), word);
+    volatile int* w = h->err_host;
+    snprintf(msg, sizeof msg, "device error: sync=%s watchdog=%d (first mbarrier wait that timed out, layer_engine.cuh WD_*; stuck roles: "
+             "producers %d, umma %d, epilogue %d, noise %d, discard %d)", cudaGetErrorString(e), word, w[1], w[2], w[3], w[4], w[6]);
     return sdrm_fail(SDRM_ERR_CUDA, msg);
   }
   return SDRM_OK;
@@ -600,13 +620,42 @@ static void probe_geometry(int64_t M, int K, int N, Geom* g, size_t* act, size_t
   *total = off;
 }
 
-static int g_probe_repeat = 1;
-void sdrm_probe_set_repeat(int n) { g_probe_repeat = n < 1 ? 1 : n; }
-void sdrm_debug_set_flags(int f) { g_debug_flags = f; }
-void sdrm_debug_set_trace(void* d_buf) { g_trace = static_cast<unsigned long long*>(d_buf); }
-void sdrm_set_cluster_override(int c) { g_cluster_override = (c == 1 || c == 2 || c == 4 || c == 8) ? c : 0; }
-void sdrm_set_subtile_override(int n) { g_subtile_override = (n == 1 || n == 2) ? n : 0; }
-void sdrm_debug_set_grid_limit(int ctas) { g_grid_limit = ctas > 0 ? ctas : 0; }
+int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
+  if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: null handle");
+  const int v = static_cast<int>(value);
+  switch (option) {
+    case SDRM_OPT_CLUSTER:
+      if (!(v == 0 || v == 1 || v == 2 || v == 4 || v == 8)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: cluster must be 0, 1, 2, 4 or 8");
+      h->cluster_override = v;
+      return SDRM_OK;
+    case SDRM_OPT_SUBTILES:
+      if (v < 0 || v > 2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: subtiles must be 0, 1 or 2");
+      h->subtile_override = v;
+      return SDRM_OK;
+    case SDRM_OPT_GRID_LIMIT:
+      h->grid_limit = v > 0 ? v : 0;
+      return SDRM_OK;
+    case SDRM_OPT_NO_DISCARD:
+      h->no_discard = v != 0;
+      return SDRM_OK;
+    case SDRM_OPT_DEBUG_FLAGS:
+#ifdef SDRM_PERF_DEBUG
+      h->debug_flags = v;
+      return SDRM_OK;
+#else
+      return v == 0 ? SDRM_OK : sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_set_option: debug flags need a -DSDRM_PERF_DEBUG build");
+#endif
+    case SDRM_OPT_TRACE_BUFFER:
+#ifdef SDRM_TRACE
+      h->trace = reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(value));
+      return SDRM_OK;
+#else
+      return value == 0 ? SDRM_OK : sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_set_option: the event timeline needs a -DSDRM_TRACE build");
+#endif
+    default:
+      return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: unknown option");
+  }
+}
 int sdrm_resident_ctas(const sdrm_handle* h, int cluster) { return (h && cluster >= 1 && cluster <= 8) ? h->resident[cluster] : 0; }
 int sdrm_last_cluster_size(const sdrm_handle* h) { return h ? h->last_cluster : 0; }
 
@@ -655,11 +704,7 @@ int sdrm_probe_linear(const float* d_A, const float* d_W, const float* d_bias, f
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(n_tiles, sms)));
   rc = fill_act_maps(P, static_cast<size_t>(n_tiles) * 2 * act);
   if (rc) return rc;
-  for (int rep = 0; rep < g_probe_repeat; ++rep) {
-    rc = launch_engine(P, grid, 1, st);
-    if (rc) return rc;
-  }
-  return SDRM_OK;
+  return launch_engine(P, grid, 1, st);
 }
 
 }  // extern "C"

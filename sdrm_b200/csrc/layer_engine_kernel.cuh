@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
-  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 2);   // mbarriers of a CTA (map below)
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6);   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
   constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   uint8_t* smem = smem_raw + (base_addr - raw_addr);
   const uint32_t bar_base = base_addr + NSTG * STG_BYTES;
   // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | (unused NSTG) | acc_full[2] | acc_empty[2] | tile_ready |
-  //                             act_chunk[MAX_SUB][MAX_ACT_CHUNKS] | state_ready[MAX_SUB] | noise_ready[MAX_SUB]
+  //                             act_chunk[MAX_SUB][MAX_ACT_CHUNKS] | state_ready[MAX_SUB] | noise_ready[MAX_SUB] |
+  //                             layer_consumed[MAX_SUB][2] | discard_done[MAX_SUB][2]
   auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
   auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
   auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
@@ -146,6 +147,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   auto bar_act_chunk = [&](uint32_t s, uint32_t c) { return bar_base + 8u * (3 * NSTG + 5 + s * MAX_ACT_CHUNKS + c); };
   auto bar_state_ready = [&](uint32_t s) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + s); };            // epilogue -> noise warps
   auto bar_noise_ready = [&](uint32_t s) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + MAX_SUB + s); };  // noise warps -> epilogue
+  // dead-buffer discard (pair mode): the UMMA issuer commits `layer_consumed` behind a chain layer's last UMMA (its input image
+  // has been read for the last time), the discard warp drops those lines from the L2 and signals `discard_done`, which the
+  // epilogue warps check before the NEXT layer's first store into that buffer
+  // Both are rings of TWO barriers per sub-tile, indexed by the low bit of the sub-tile's layer count k (parity = bit 1 of k):
+  // with interleaved sub-tiles the UMMAs of a two-chunk layer can retire a whole layer ahead of the epilogue, so up to two
+  // phases of a sub-tile are outstanding and a single barrier would be lapped (parity aliasing = deadlock).
+  auto bar_layer_consumed = [&](uint32_t s, uint32_t k) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + 2 * MAX_SUB + 2 * s + (k & 1u)); };
+  auto bar_discard_done = [&](uint32_t s, uint32_t k) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + 4 * MAX_SUB + 2 * s + (k & 1u)); };
+  // per-role layer counters: two bits per sub-tile (k mod 4 is all the ring index and the parity need)
+  auto cnt_get = [](uint32_t cnt, int s) -> uint32_t { return (cnt >> (2 * s)) & 3u; };
+  auto cnt_inc = [](uint32_t cnt, int s) -> uint32_t { return (cnt & ~(3u << (2 * s))) | ((((cnt >> (2 * s)) + 1u) & 3u) << (2 * s)); };
   uint8_t* misc = smem + NSTG * STG_BYTES + 8 * NBAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
@@ -172,6 +184,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), EPI_WARPS);
       mbar_init(bar_state_ready(s), EPI_WARPS);
       mbar_init(bar_noise_ready(s), NOISE_WARPS);
+      for (uint32_t k = 0; k < 2; ++k) {
+        mbar_init(bar_layer_consumed(s, k), 1);
+        mbar_init(bar_discard_done(s, k), 1);
+      }
     }
     mbar_init(bar_tile_ready, EPI_WARPS);
     fence_mbar_init();
@@ -344,7 +360,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     } else {
       // ======================================= UMMA issuer ========================================
       // whole warp converged, one elected lane issues (see the producer comment)
-      uint32_t stage = 0, sphase = 0, cc = 0;
+      uint32_t stage = 0, sphase = 0, cc = 0, lc_cnt = 0;
       for (int it = 0; it < n_iters; ++it) {
         if (!PAIR && tile_of(it, 0) >= n_tiles) break;
         const int ns = nsub_of(it);
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait(bar_tile_ready, it & 1, err, WD_MMA_TILE);
           T_tile = tile_T[it & 1];
         }
-        auto run = [&](const LayerDesc& ldref) {
+        auto run = [&](const LayerDesc& ldref, int s, bool chain) {
           const int KB = ldref.KB, NCH = ldref.NCH, passes = ldref.passes, kmma_last = ldref.kmma_last;
           const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ldref.NC);
           for (int c = 0; c < NCH; ++c) {
@@ -403,16 +419,56 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             SDRM_TR(1, 4);
             ++cc;
           }
+          if (PAIR && chain && P.discard_kb > 0) {
+            // every UMMA of this layer has retired when this arrives: the layer's input image is dead
+            if (elect_one()) umma_commit_pair(bar_layer_consumed(s, cnt_get(lc_cnt, s)), static_cast<uint16_t>(0x3u << leader_rank));
+            __syncwarp();
+            lc_cnt = cnt_inc(lc_cnt, s);
+          }
         };
         for (int i = T_tile; i >= 1; --i)
           for (int l = 0; l < P.n_step; ++l)
-            for (int s = 0; s < ns; ++s) run(P.step[l]);
+            for (int s = 0; s < ns; ++s) run(P.step[l], s, true);
         for (int l = 0; l < P.n_dec; ++l)
-          for (int s = 0; s < ns; ++s) run(P.dec[l]);
+          for (int s = 0; s < ns; ++s) run(P.dec[l], s, false);
       }
     }
   } else if (warp > A_WARP) {
-    setmaxnreg_dec<REGS_CTRL>();   // idle fourth warp of the control warpgroup
+    setmaxnreg_dec<REGS_CTRL>();
+    // ======================================= discard warp (fourth control warp) =================================
+    // A chain layer's input image is dead once the layer's last UMMA has read it, but its lines are DIRTY in the L2 and, with
+    // 148 x 0.98 MB of scratch against ~60 MB of effective L2, they are written back to HBM before the layer after next
+    // overwrites them: 1.47 MB of DRAM writes per CTA and step for data nobody will read (ncu: 93 % of all bytes the kernel
+    // writes reach DRAM).  discard.global.L2 drops such lines without a write-back (tools/ubench_discard.cu: 15.4 GB -> 0.5 GB of
+    // DRAM writes).  Only whole k-blocks that the next writer rewrites completely are discarded (discard_kb), so the zero
+    // padding columns written once at kernel start survive.
+    if (PAIR && P.discard_kb > 0) {
+      uint32_t dcnt = 0;   // layer counters of the sub-tiles
+      const int n_lines = P.discard_kb * (A_TILE_BYTES / 128);
+      for (int it = 0; it < n_iters; ++it) {
+        const int ns = nsub_of(it);
+        int cur = 0;
+        for (int i = P.T; i >= 1; --i)
+          for (int l = 0; l < P.n_step; ++l) {
+            for (int s = 0; s < ns; ++s) {
+              const uint32_t k = cnt_get(dcnt, s);
+              dcnt = cnt_inc(dcnt, s);
+              mbar_wait(bar_layer_consumed(s, k), (k >> 1) & 1u, err, WD_DISCARD);
+              if (!(i == 1 && l == P.n_step - 1)) {   // (the last chain layer's neighbours are the decoder's buffers: left alone)
+                uint8_t* dead = scratch_of(tile_of(it, s), s) + static_cast<size_t>(cur) * P.act_buf_bytes;
+#ifndef SDRM_DISCARD_DRY   // (debug builds: the barrier protocol without the discards)
+                for (int j = lane; j < n_lines; j += 32)
+                  asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + static_cast<size_t>(j) * 128) : "memory");
+#endif
+                fence_proxy_async();   // the next writes to these lines are TMA stores (async proxy)
+              }
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_discard_done(s, k));
+            }
+            cur ^= 1;
+          }
+      }
+    }
   } else if (warp < EPI_WARPS) {
     // ======================================= epilogue warps =====================================
     // 16 warps: warp (q, sub) reads TMEM lane quarter q (rows 32q..32q+31) and owns the 16-column groups
@@ -508,6 +564,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       epi_bar_sync();
     }
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
+    uint32_t dd_cnt = 0;      // discard_done phases consumed per sub-tile (two bits each)
     // context of the sub-tile a layer works on (set_ctx): scratch pointers are recomputed, the row facts are kept per sub-tile
     uint8_t* sc = nullptr;
     float* xs = nullptr;
@@ -528,7 +585,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         valid = prow < P.n_rows;
         row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;  // logical row
         t_row = P.T;
-        if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
+        if (P.t_start) t_row = valid ? min(max(P.t_start[prow], 0), P.T) : 0;   // clamped: an out-of-range entry must not index bias0 / coef out of bounds
       };
 
       // ---- row facts of every sub-tile; tile start step = max over rows (and sub-tiles)
@@ -832,13 +889,28 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           default: run(std::integral_constant<int, EPI_LINEAR_OUT>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
         }
       };
+      // a layer writes into the buffer the PREVIOUS layer of the same sub-tile read: that layer's dead lines must have been
+      // discarded first (long done by then: the discard follows the previous layer's last UMMA, this follows its last epilogue)
+      const bool discarding = PAIR && P.discard_kb > 0;
+      uint32_t dd_pending = 0;   // bit s: a chain layer of sub-tile s has run in this tile
+      auto discard_gate = [&](int s) {
+        if (discarding && ((dd_pending >> s) & 1u)) {
+          const uint32_t k = cnt_get(dd_cnt, s);
+          dd_cnt = cnt_inc(dd_cnt, s);
+          mbar_wait(bar_discard_done(s, k), (k >> 1) & 1u, err, WD_EPI_DISCARD);
+        }
+      };
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
         for (int l = 0; l < P.n_step; ++l) {
-          for (int s = 0; s < ns; ++s)
+          for (int s = 0; s < ns; ++s) {
+            discard_gate(s);
             run_kind(P.step[l], i, (P.n_dec == 0) && (i == 1) && (l == P.n_step - 1), cur ^ 1, 2, s);   // x0 lo -> buffer 2
+            dd_pending |= 1u << s;
+          }
           cur ^= 1;
         }
+      for (int s = 0; s < ns; ++s) discard_gate(s);   // the last chain layer's phase (keeps the parities in step across tiles)
       for (int l = 0; l < P.n_dec; ++l)
         for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s);
     }
@@ -872,7 +944,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const long long row = (valid && P.row_ids) ? static_cast<long long>(P.row_ids[prow]) : prow;
         const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
         int t_row = P.T;
-        if (P.t_start) t_row = valid ? P.t_start[prow] : 0;
+        if (P.t_start) t_row = valid ? min(max(P.t_start[prow], 0), P.T) : 0;   // clamped: an out-of-range entry must not index bias0 / coef out of bounds
         if (i != T_tile) {
           mbar_wait_sleepy(bar_state_ready(s), (st_par >> s) & 1u, err, WD_NOISE_STATE, 128);
           st_par ^= 1u << s;

@@ -40,23 +40,35 @@ class SamplerEngine:
             pass
 
     # ---------------------------------------------------------------------------------------------
+    # Weight packing.  The packed images are rebuilt on EVERY call by default: the pack kernels cost ~0.1 ms, and no host-side
+    # key can see an in-place edit through `.data` (EMA swaps, `p.data.copy_()`, a new module allocated at recycled addresses
+    # with the same version counters), which would silently sample from stale weights.  A caller that guarantees unchanged
+    # weights between calls (e.g. main.py's two samplings of one trained model) may opt into reuse with `reuse_packed=True`;
+    # `invalidate()` drops the cached key.  Nothing here reads device memory on the host (no hidden synchronisation).
     @staticmethod
     def _key(tensors, extra):
         return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors if t is not None) + tuple(extra)
 
-    def pack_denoiser(self, diff_net, schedule, noise_divider, force=False):
-        """diff_net: sdrm_b200.models.SDRM (or any module with the same layer_tensors()); schedule = (b_t,a_t,ab_t)."""
+    def invalidate(self):
+        self._den_key = None
+        self._dec_key = None
+
+    def pack_denoiser(self, diff_net, schedule, noise_divider, force=True):
+        """diff_net: sdrm_b200.models.SDRM (or any module with the same layer_tensors()); schedule = (b_t,a_t,ab_t).
+        force=False skips the re-pack when the parameter tensors (address, version counter, shape) and the schedule tensors
+        are the ones packed last time."""
         lt = diff_net.layer_tensors()
         T = diff_net.EMB_DIM
         D, in_dim = lt["W0"].shape
         L = in_dim - T
         nh = diff_net.n_hidden_layers
-        sched = torch.cat([s.detach().to(self.device, torch.float32).reshape(-1) for s in schedule]).contiguous()
-        if sched.numel() != 3 * (T + 1):
-            raise ValueError(f"schedule must have 3*(T+1)={3 * (T + 1)} entries, got {sched.numel()}")
-        key = self._key(list(lt.values()), (float(noise_divider), T, L, D, nh, tuple(sched.tolist())))
+        for s_ in schedule:
+            if s_.numel() != T + 1:
+                raise ValueError(f"schedule tensors must have T+1={T + 1} entries, got {s_.numel()}")
+        key = self._key(list(lt.values()) + list(schedule), (float(noise_divider), T, L, D, nh))
         if not force and key == self._den_key:
             return
+        sched = torch.cat([s_.detach().to(self.device, torch.float32).reshape(-1) for s_ in schedule]).contiguous()
         ts = {k: (_f32c(v.to(self.device)) if v is not None else None) for k, v in lt.items()}
         st = _lib.stream_ptr()
         rc = self.lib.sdrm_denoiser_pack(
@@ -68,7 +80,7 @@ class SamplerEngine:
         self._den_key = key
         self.T, self.L = T, L
 
-    def pack_decoder(self, vae_net, force=False):
+    def pack_decoder(self, vae_net, force=True):
         W1, b1 = vae_net.decoder[0].weight, vae_net.decoder[0].bias
         W2, b2 = vae_net.decoder[2].weight, vae_net.decoder[2].bias
         H, L = W1.shape
@@ -103,9 +115,11 @@ class SamplerEngine:
             return out
         ws, need = self.workspace(n)
         if t_start is not None:
-            t_start = t_start.to(self.device, torch.int32).contiguous()
             if t_start.numel() != n:
                 raise ValueError("t_start must have n entries")
+            if t_start.device.type == "cpu" and t_start.numel() and (int(t_start.min()) < 0 or int(t_start.max()) > self.T):
+                raise ValueError(f"t_start entries must lie in [0, T={self.T}]")   # (device tensors are clamped by the kernel)
+            t_start = t_start.to(self.device, torch.int32).contiguous()
         if row_ids is not None:
             row_ids = row_ids.to(self.device, torch.int32).contiguous()
             if row_ids.numel() != n:
@@ -121,6 +135,10 @@ class SamplerEngine:
         if check:
             _lib.check(self.lib.sdrm_check_device_error(self.handle, _lib.stream_ptr()), "sdrm_sample (device)")
         return out
+
+    def set_option(self, option, value):
+        """Per-handle tuning option (include/sdrm_b200.h enum sdrm_option; _lib.OPT_*).  0 = automatic."""
+        _lib.check(self.lib.sdrm_set_option(self.handle, int(option), int(value)), "sdrm_set_option")
 
     def launch_count(self):
         return int(self.lib.sdrm_last_launch_count(self.handle))

@@ -17,18 +17,11 @@ def _dev():
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def topk_device(scores, k, return_values=False):
-    """scores: CUDA float32/float64 [rows, I] (row stride arbitrary) -> int32 [rows, k] sorted indices."""
-    if k < 1 or k > MAX_K:
-        raise NotImplementedError(f"k={k}: the warp top-k kernel supports 1 <= k <= {MAX_K}")
-    if scores.dim() != 2 or scores.stride(1) != 1:
-        scores = scores.contiguous()
+def _topk_pass(scores, k, want_vals):
     rows, n_items = scores.shape
-    if k > n_items:
-        raise ValueError("k larger than the number of items")
     lib = _lib.load()
     idx = torch.empty((rows, k), dtype=torch.int32, device=scores.device)
-    vals = torch.empty((rows, k), dtype=scores.dtype, device=scores.device) if return_values else None
+    vals = torch.empty((rows, k), dtype=scores.dtype, device=scores.device) if want_vals else None
     if scores.dtype == torch.float32:
         fn = lib.sdrm_topk
     elif scores.dtype == torch.float64:
@@ -37,7 +30,38 @@ def topk_device(scores, k, return_values=False):
         raise TypeError("scores must be float32 or float64")
     _lib.check(fn(_lib.ptr(scores), rows, n_items, scores.stride(0), k, _lib.ptr(idx), _lib.ptr(vals),
                   _lib.stream_ptr()), "sdrm_topk")
-    return (idx, vals) if return_values else idx
+    return idx, vals
+
+
+def topk_device(scores, k, return_values=False):
+    """scores: CUDA float32/float64 [rows, I] (row stride arbitrary) -> int32 [rows, k] sorted indices.
+
+    k <= 64 is one pass of the warp kernel.  Larger k (the reference wrappers default to k=100, utilities.py:123,149) takes
+    ceil(k / 64) passes over a working copy in which the entries already emitted are lowered to -inf; the concatenation is
+    the same descending / lower-index-first order.  (Rows with fewer than k entries above -inf list -inf entries at the end,
+    whose order is arbitrary in the reference's argpartition too.)"""
+    if k < 1:
+        raise ValueError("k must be >= 1")
+    if scores.dim() != 2 or scores.stride(1) != 1:
+        scores = scores.contiguous()
+    rows, n_items = scores.shape
+    if k > n_items:
+        raise ValueError("k larger than the number of items")
+    if k <= MAX_K:
+        idx, vals = _topk_pass(scores, k, return_values)
+        return (idx, vals) if return_values else idx
+    work = scores.clone()
+    idx_parts, val_parts, left = [], [], k
+    while left > 0:
+        kk = min(MAX_K, left)
+        idx, vals = _topk_pass(work, kk, return_values)
+        idx_parts.append(idx)
+        val_parts.append(vals)
+        left -= kk
+        if left > 0:
+            work.scatter_(1, idx.long(), float("-inf"))
+    idx = torch.cat(idx_parts, dim=1)
+    return (idx, torch.cat(val_parts, dim=1)) if return_values else idx
 
 
 def _counters(X_pred, heldout, k):

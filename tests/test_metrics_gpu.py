@@ -29,6 +29,20 @@ def test_topk_indices_bit_exact(rows, items, k):
     assert np.array_equal(vals.cpu().numpy(), np.take_along_axis(x, ref, axis=1))
 
 
+@pytest.mark.parametrize("k", [65, 100, 150])
+def test_topk_above_64_multi_pass(k):
+    """the reference wrappers default to k=100 (utilities.py:123,149): ceil(k/64) passes of the warp kernel"""
+    from sdrm_b200 import metrics
+    x = _scores(37, 1008, seed=k, ties=(k == 100))
+    idx = metrics.topk_device(torch.from_numpy(x).cuda(), k).cpu().numpy()
+    assert np.array_equal(idx, orc.topk_oracle(x, k))
+    held = (np.random.RandomState(k).rand(37, 1008) < 0.05).astype(np.float32)
+    r = metrics.recall_at_k_batch(torch.from_numpy(x).cuda(), held)          # default k = 100 like the reference
+    ref_idx = orc.topk_oracle(x, 100)
+    hits = np.take_along_axis(held, ref_idx, axis=1).sum(axis=1).astype(np.float32)
+    assert np.array_equal(r, hits / np.minimum(100, held.sum(axis=1).astype(np.int64)))
+
+
 def test_topk_ties_neg_inf_nan_and_strided_rows():
     from sdrm_b200 import metrics
     x = _scores(50, 400, seed=1, ties=True)

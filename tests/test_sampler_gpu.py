@@ -96,11 +96,11 @@ def test_single_and_pair_mode_are_bit_identical():
         for c in (1, 2, 4, 8):
             if lib.sdrm_resident_ctas(eng.handle, c) < c:
                 continue
-            lib.sdrm_set_cluster_override(c)
+            eng.set_option(_lib.OPT_CLUSTER, c)
             outs[c] = eng.sample(n, seed=77, check=True).clone()
             assert lib.sdrm_last_cluster_size(eng.handle) == c
     finally:
-        lib.sdrm_set_cluster_override(0)
+        eng.set_option(_lib.OPT_CLUSTER, 0)
     assert 1 in outs and 2 in outs and 4 in outs
     for c in outs:
         assert torch.equal(outs[1], outs[c]), c
@@ -121,18 +121,18 @@ def test_interleaved_sub_tiles_are_bit_identical():
         for cluster, limit in ((2, 4), (2, 8), (4, 4)):
             if lib.sdrm_resident_ctas(eng.handle, cluster) < cluster:
                 continue
-            lib.sdrm_set_cluster_override(cluster)
-            lib.sdrm_debug_set_grid_limit(limit)
+            eng.set_option(_lib.OPT_CLUSTER, cluster)
+            eng.set_option(_lib.OPT_GRID_LIMIT, limit)
             for sub in (1, 2):
-                lib.sdrm_set_subtile_override(sub)
+                eng.set_option(_lib.OPT_SUBTILES, sub)
                 lat = torch.empty(n, L, device="cuda")
                 out = eng.sample(n, seed=77, latent_out=lat, check=True)
                 assert torch.equal(out, ref), (cluster, limit, sub)
                 assert torch.equal(lat, lat_ref), (cluster, limit, sub)
     finally:
-        lib.sdrm_set_cluster_override(0)
-        lib.sdrm_debug_set_grid_limit(0)
-        lib.sdrm_set_subtile_override(0)
+        eng.set_option(_lib.OPT_CLUSTER, 0)
+        eng.set_option(_lib.OPT_GRID_LIMIT, 0)
+        eng.set_option(_lib.OPT_SUBTILES, 0)
 
 
 def test_random_mode_matches_oracle():

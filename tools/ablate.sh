@@ -15,9 +15,9 @@ except Exception as e:
 PY
 }
 run base libdbg.so 0 ""
-run no-noise libdbg.so 4 ""
+run noise-no-rng libdbg.so 16 ""
+run noise-no-state libdbg.so 32 ""
+run act-store-fixed libdbg.so 64 ""
+run no-store-wait libdbg.so 128 ""
 run no-act-stores libdbg.so 1 ""
-run no-noise-no-act-stores libdbg.so 5 ""
-run cluster4 libsdrm_b200.so 0 "--cluster 4"
-run cluster8 libsdrm_b200.so 0 "--cluster 8"
-run cluster2 libsdrm_b200.so 0 "--cluster 2"
+run base2 libdbg.so 0 ""

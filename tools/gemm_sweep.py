@@ -12,13 +12,12 @@ def run(M, K, N, split3=0, reps=(1, 9)):
     wsb = lib.sdrm_probe_linear_workspace_bytes(M, K, N); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
     ts = []
     for rep in reps:
-        lib.sdrm_probe_set_repeat(rep)
         for _ in range(2):
             torch.cuda.synchronize(); t0 = time.perf_counter()
-            _lib.check(lib.sdrm_probe_linear(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(out), M, K, N, split3, _lib.ptr(ws), wsb, _lib.stream_ptr()))
+            for _r in range(rep):
+                _lib.check(lib.sdrm_probe_linear(_lib.ptr(A), _lib.ptr(W), _lib.ptr(b), _lib.ptr(out), M, K, N, split3, _lib.ptr(ws), wsb, _lib.stream_ptr()))
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
         ts.append(dt)
-    lib.sdrm_probe_set_repeat(1)
     t = (ts[1] - ts[0]) / (reps[1] - reps[0])
     passes = 3 if split3 else 1
     nch = (N + 255) // 256; nc = -(-(-(-N // nch)) // 16) * 16

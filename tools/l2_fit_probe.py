@@ -1,4 +1,4 @@
-"""Does the engine's DRAM traffic come from L2 capacity?  One full wave of cfg-5 row tiles on GRID CTAs (sdrm_debug_set_grid_limit):
+"""Does the engine's DRAM traffic come from L2 capacity?  One full wave of cfg-5 row tiles on GRID CTAs (SDRM_OPT_GRID_LIMIT):
    python tools/l2_fit_probe.py GRID [waves]            -> ms per wave (CUDA events)
    ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,\
 gpu__time_duration.sum,lts__t_sector_hit_rate.pct -k regex:layer_engine python tools/l2_fit_probe.py GRID 1
@@ -11,15 +11,14 @@ import torch
 
 import bench
 from sdrm_b200 import _lib
-from sdrm_b200.train_SDRM import sample_ddpm
+from sdrm_b200.train_SDRM import engine_for, sample_ddpm
 
 grid = int(sys.argv[1])
 waves = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 w = bench.WORKLOADS["cfg5"]
 dev = torch.device("cuda", 0)
 diff, vae = bench.build_models(w, dev)
-lib = _lib.load()
-lib.sdrm_debug_set_grid_limit(grid)
+engine_for(diff, dev).set_option(_lib.OPT_GRID_LIMIT, grid)
 n = grid * 128 * waves
 out = torch.empty((n, w["I"]), dtype=torch.float32, device=dev)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

@@ -7,16 +7,17 @@ from sdrm_b200 import _lib
 from sdrm_b200.train_SDRM import sample_ddpm, engine_for
 w = dict(WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg5"]); w["T"] = 4
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 18944
-lib = _lib.load(); lib.sdrm_set_cluster_override(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
-lib.sdrm_debug_set_flags(int(os.environ.get('SDRM_DEBUG_FLAGS', '0')))
 diff, vae = build_models(w, "cuda")
+eng = engine_for(diff, "cuda")   # needs a -DSDRM_TRACE (and, for the flags, -DSDRM_PERF_DEBUG) build selected with SDRM_B200_LIB
+eng.set_option(_lib.OPT_CLUSTER, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+eng.set_option(_lib.OPT_DEBUG_FLAGS, int(os.environ.get('SDRM_DEBUG_FLAGS', '0')))
 CAP = 8192
 buf = torch.zeros(3 * CAP, dtype=torch.int64, device="cuda")
 out = sample_ddpm(rows, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=1)
 torch.cuda.synchronize()
-lib.sdrm_debug_set_trace(_lib.ptr(buf))
+eng.set_option(_lib.OPT_TRACE_BUFFER, buf.data_ptr())
 out = sample_ddpm(rows, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=2)
-torch.cuda.synchronize(); lib.sdrm_debug_set_trace(None)
+torch.cuda.synchronize(); eng.set_option(_lib.OPT_TRACE_BUFFER, 0)
 ev = buf.cpu().numpy().astype("uint64").reshape(3, CAP)
 names = {0: {1: "P.layer_begin", 2: "P.act_ready", 3: "P.chunk_issued", 4: "P.empty_ok", 5: "P.issued"}, 1: {1: "M.chunk_begin", 2: "M.acc_free", 3: "M.first_full", 4: "M.chunk_committed", 5: "M.full_ok", 6: "M.kb_issued", 7: "M.local_full_ok"},
          2: {1: "E.wait", 2: "E.acc_full", 3: "E.chunk_done", 4: "E.noise_done", 5: "E.layer_done"}}

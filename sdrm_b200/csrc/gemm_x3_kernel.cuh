@@ -15,7 +15,8 @@
 // K = 16).  Each CTA stages its own 128 rows of A (hi + lo) and HALF of the B tile (hi + lo): a 64-wide k-block is 64 KB per
 // CTA and serves 3 x 4 UMMAs (1536 tensor cycles) = 42 B/clk of L2 -> SM traffic per SM, under the SM's ~64 B/clk port.
 // Three such stages; two 256-column accumulators in TMEM so the epilogue of tile i overlaps the UMMAs of tile i+1.
-// warp 0 = TMA producer, warp 1 = UMMA issuer (leader CTA) + TMEM allocation, warps 2-5 = epilogue (one TMEM lane quarter each).
+// warp 0 = TMA producer, warp 1 = UMMA issuer (leader CTA) + TMEM allocation, warps 2-9 = epilogue (two per TMEM lane quarter,
+// alternating 16-column groups; the next group's accumulator columns and PReLU' inputs are requested one group ahead).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -57,7 +58,8 @@ struct GemmParams {
   int* err_word;
 };
 
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;                 // two per TMEM lane quarter: the epilogue is latency-bound (aux / bias loads, stores)
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_NSTG = 3;
 constexpr uint32_t GEMM_TILE_A = 128 * 128;                 // one 128-row x 64-column bf16 operand image
 constexpr uint32_t GEMM_STG_BYTES = 4 * GEMM_TILE_A;        // A hi | A lo | B hi (<= 128 rows) | B lo
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(bar_acc_full(b), 1);
-      mbar_init(bar_acc_empty(b), 8);   // 4 epilogue warps of each CTA
+      mbar_init(bar_acc_empty(b), 2 * GEMM_EPI_WARPS);   // the epilogue warps of both CTAs
     }
     fence_mbar_init();
   }
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
     for (long long wk = my_cluster; wk < n_work; wk += n_clusters) {
       const int split = static_cast<int>(wk / tiles_mn);
       const long long tmn = wk - split * tiles_mn;
-      const int mt = static_cast<int>(tmn % P.m_tiles), nt = static_cast<int>(tmn / P.m_tiles);
+      const int mt = static_cast<int>(tmn / P.n_tiles), nt = static_cast<int>(tmn % P.n_tiles);   // n fastest: the clusters running together share A row blocks (L2 hits)
       const int a_row = mt * 256 + static_cast<int>(rank) * 128;
       const int b_row = nt * P.BN + static_cast<int>(rank) * (P.BN / 2);
       const int kb0 = split * P.kb_per_split, kb1 = min(P.kb_total, kb0 + P.kb_per_split);
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
   } else {
     // ================================ epilogue warps (both CTAs) ================================
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;             // which of the quarter's warps: owns the column groups g = sub (mod 2)
     const int r = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
     uint32_t cc = 0;
@@ -190,7 +193,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
     for (long long wk = my_cluster; wk < n_work; wk += n_clusters) {
       const int split = static_cast<int>(wk / tiles_mn);
       const long long tmn = wk - split * tiles_mn;
-      const int mt = static_cast<int>(tmn % P.m_tiles), nt = static_cast<int>(tmn / P.m_tiles);
+      const int mt = static_cast<int>(tmn / P.n_tiles), nt = static_cast<int>(tmn % P.n_tiles);   // n fastest: the clusters running together share A row blocks (L2 hits)
       const long long row = static_cast<long long>(mt) * 256 + rank * 128 + r;
       const bool row_ok = row < P.M;
       const uint32_t buf = cc & 1u;
@@ -200,18 +203,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
       if (P.bias_table && row_ok) brow = P.bias_table + P.bias_rows[row] * P.bias_ld;
       const float* arow = (P.aux && row_ok) ? P.aux + row * P.ld_aux : nullptr;
       float tile_ds = 0.0f;
+      // PReLU' inputs of this warp's first group: they do not depend on the accumulator, so they are in flight during the wait
+      const bool aux_vec = arow && ((P.ld_aux & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.aux) & 15) == 0);
+      float an[16];
+      auto load_aux = [&](int g) {
+        const int c0 = nt * P.BN + g * 16;
+        if (!arow || c0 >= P.N) return;
+        if (aux_vec && c0 + 16 <= P.N) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 q4 = __ldcs(reinterpret_cast<const float4*>(arow + c0) + j);
+            an[4 * j] = q4.x; an[4 * j + 1] = q4.y; an[4 * j + 2] = q4.z; an[4 * j + 3] = q4.w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) an[e] = (c0 + e < P.N) ? arow[c0 + e] : 1.0f;
+        }
+      };
+      load_aux(sub);
       mbar_wait(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_G_EPI);
       tc_fence_after();
       const uint32_t t_tile = tmem_base + lane_addr + buf * 256u;
       uint32_t v[16];
-      tmem_ld16(t_tile, v);
-      for (int g = 0; g < ngroups; ++g) {
+      if (sub < ngroups) tmem_ld16(t_tile + sub * 16u, v);
+      for (int g = sub; g < ngroups; g += GEMM_EPI_WARPS / 4) {
         const int col0 = nt * P.BN + g * 16;
         tmem_ld_wait();
-        float h[16];
+        float h[16], a16[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) h[e] = __uint_as_float(v[e]);
-        if (g + 1 < ngroups) tmem_ld16(t_tile + (g + 1) * 16u, v);
+        for (int e = 0; e < 16; ++e) { h[e] = __uint_as_float(v[e]); a16[e] = an[e]; }
+        if (g + GEMM_EPI_WARPS / 4 < ngroups) {
+          tmem_ld16(t_tile + (g + GEMM_EPI_WARPS / 4) * 16u, v);
+          load_aux(g + GEMM_EPI_WARPS / 4);
+        }
         if (!row_ok || col0 >= P.N) continue;
         const bool full = col0 + 16 <= P.N;
         if (P.bias || brow) {
@@ -230,7 +254,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) sdrm_gemm_pair_kernel(const _
         } else if (P.epi == GEMM_EPI_DPRELU) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const float a = (full || col0 + e < P.N) ? arow[col0 + e] : 1.0f;
+            const float a = (full || col0 + e < P.N) ? a16[e] : 1.0f;
             tile_ds += h[e] * fminf(a, 0.0f);
             h[e] = a > 0.0f ? h[e] : slope * h[e];
             o[e] = h[e];

@@ -6,8 +6,8 @@
 // the epilogue, the backward is one data-gradient GEMM (PReLU' fused) and one split-K weight-gradient GEMM per layer; the
 // shared hidden Linear (train_SDRM.py:94) accumulates its gradient over its nh applications in ONE slab reduction.
 //
-// Exports: sdrm_denoiser_train_workspace_bytes / sdrm_denoiser_fwd / sdrm_denoiser_bwd and the unit-test
-// entry sdrm_gemm_nt.
+// Exports: sdrm_denoiser_train_workspace_bytes / sdrm_denoiser_fwd / sdrm_denoiser_bwd and the plain product
+// sdrm_gemm (the three products of a Linear layer and its autograd: MultiVAE++ training step, unit tests).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -338,18 +338,29 @@ Bf16Mat mat_at(uint8_t* ws, size_t off, long long rows, long long cols, long lon
 
 extern "C" {
 
-size_t sdrm_gemm_nt_workspace_bytes(int64_t M, int N, int K, int splits) {
+// automatic split-K factor (splits == 0): enough work items for the resident clusters when the output has few tiles
+static int auto_splits(int64_t M, int N, int64_t K) {
+  int clusters = 0;
+  if (gemm_clusters(&clusters)) return 1;
+  return wgrad_splits(M, N, K, clusters);
+}
+
+size_t sdrm_gemm_workspace_bytes(int64_t M, int N, int64_t K, int splits) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (splits == 0) splits = 8;   // upper bound of the automatic choice
   const long long Kp = up64(K);
   return 256 + bf_pair_bytes(M, Kp) + bf_pair_bytes(N, Kp) + (splits > 1 ? static_cast<size_t>(splits) * M * up64(N) * 4 : 0) + 1024;
 }
 
-int sdrm_gemm_nt(const float* d_A, int64_t lda, const float* d_B, int64_t ldb, const float* d_bias, float* d_C, int64_t ldc,
-                 int64_t M, int N, int K, int passes, int splits, void* d_workspace, size_t workspace_bytes, void* stream) {
-  if (!d_A || !d_B || !d_C || !d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_gemm_nt: null pointer");
-  if (M <= 0 || N <= 0 || K <= 0 || lda < K || ldb < K || ldc < N) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_gemm_nt: bad shape");
-  if (splits < 1) splits = 1;
-  if (workspace_bytes < sdrm_gemm_nt_workspace_bytes(M, N, K, splits)) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_gemm_nt: workspace too small");
+int sdrm_gemm(const float* d_A, int64_t lda, int trans_a, const float* d_B, int64_t ldb, int trans_b, const float* d_bias, float* d_C,
+              int64_t ldc, int64_t M, int N, int64_t K, int passes, int splits, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (!d_A || !d_B || !d_C || !d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_gemm: null pointer");
+  if (M <= 0 || N <= 0 || K <= 0 || ldc < N || lda < (trans_a ? M : K) || ldb < (trans_b ? N : K))
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_gemm: bad shape / leading dimension");
+  if (K > 0x7fffffffLL || M > 0x7fffffffLL) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_gemm: dimension above 2^31");
+  if (splits < 0) splits = 1;
+  if (workspace_bytes < sdrm_gemm_workspace_bytes(M, N, K, splits)) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_gemm: workspace too small");
+  if (splits == 0) splits = auto_splits(M, N, K);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint8_t* ws = static_cast<uint8_t*>(d_workspace);
   const long long Kp = up64(K), Np = up64(N);
@@ -359,18 +370,27 @@ int sdrm_gemm_nt(const float* d_A, int64_t lda, const float* d_B, int64_t ldb, c
   Bf16Mat B = mat_at(ws, off, N, K, Kp); off += bf_pair_bytes(N, Kp);
   float* slabs = reinterpret_cast<float*>(ws + off);
   int rc;
-  if ((rc = launch_prep(d_A, lda, M, K, PREP_IDENT, nullptr, 0, nullptr, &A, nullptr, nullptr, st))) return rc;
-  if ((rc = launch_prep(d_B, ldb, N, K, PREP_IDENT, nullptr, 0, nullptr, &B, nullptr, nullptr, st))) return rc;
+  // an operand given transposed ([K, M] / [K, N] in memory) goes through the transposing path of the operand preparation
+  if (trans_a) rc = launch_prep(d_A, lda, K, static_cast<int>(M), PREP_IDENT, nullptr, 0, nullptr, nullptr, &A, nullptr, st);
+  else rc = launch_prep(d_A, lda, M, static_cast<int>(K), PREP_IDENT, nullptr, 0, nullptr, &A, nullptr, nullptr, st);
+  if (rc) return rc;
+  if (trans_b) rc = launch_prep(d_B, ldb, K, N, PREP_IDENT, nullptr, 0, nullptr, nullptr, &B, nullptr, st);
+  else rc = launch_prep(d_B, ldb, N, static_cast<int>(K), PREP_IDENT, nullptr, 0, nullptr, &B, nullptr, nullptr, st);
+  if (rc) return rc;
   GemmCall g;
   g.A = A; g.B = B; g.passes = passes;
-  if (splits > 1) {
-    g.C = slabs; g.ldc = Np; g.splits = splits; g.slab_stride = static_cast<long long>(M) * Np;
+  const int kb = static_cast<int>((K + 63) / 64);
+  int eff = std::max(1, std::min(splits, kb));
+  const int per = (kb + eff - 1) / eff;
+  eff = (kb + per - 1) / per;   // what launch_gemm uses
+  if (eff > 1) {
+    g.C = slabs; g.ldc = Np; g.splits = eff; g.slab_stride = static_cast<long long>(M) * Np;
   } else {
     g.C = d_C; g.ldc = ldc; g.bias = d_bias;
   }
   if ((rc = launch_gemm(g, reinterpret_cast<int*>(ws), st))) return rc;
-  if (splits > 1) {
-    const int kb = (K + 63) / 64, per = (kb + splits - 1) / splits, eff = (kb + per - 1) / per;   // what launch_gemm really used
+  if (eff > 1) {
+    if (d_bias) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_gemm: bias with split-K");
     slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, eff, Np, static_cast<int>(M), N, d_C, ldc);
     SDRM_CUDA(cudaGetLastError());
   }

@@ -232,17 +232,29 @@ def train_variational_autoencoder(model, train_data, test_data, epochs, batch_si
     kind, k = early_stop_metric.split("@")
     k = int(k)
     start_time = time.time()
+    on_gpu = dev.type == "cuda"
+    # the interaction matrix goes to the device ONCE (CSR); minibatches are row slices densified there
+    staged = training.DeviceCSR(train_data, dev) if on_gpu else None
+    n_train = train_data.shape[0]
     for epoch in range(epochs):
         losses = []
         model.train()
         model.is_training = 1
-        train_data = train_data[np.random.permutation(train_data.shape[0])]
-        for s in range(0, train_data.shape[0], batch_size):
-            e = min(s + batch_size, train_data.shape[0])
+        perm = np.random.permutation(n_train)      # same draw as the reference's train_data[np.random.permutation(...)]
+        if staged is None:
+            train_data = train_data[perm]
+        for s in range(0, n_train, batch_size):
+            e = min(s + batch_size, n_train)
             anneal = min(anneal_cap, 1.0 * anneal_count / 20_000)
-            X = torch.tensor(train_data[s:e].toarray(), dtype=torch.float32, device=dev)
+            if staged is not None:
+                X = staged.dense_rows(perm[s:e])
+            else:
+                X = torch.tensor(train_data[s:e].toarray(), dtype=torch.float32, device=dev)
             optimizer.zero_grad()
-            output, vae_kl = model(X)
+            if on_gpu:
+                output, vae_kl = training.vae_forward_tc(model, X)   # the four Linear layers on the tcgen05 GEMM (fwd + bwd)
+            else:
+                output, vae_kl = model(X)
             neg_ll = training.multinomial_nll(output, X)   # fused log-softmax NLL (train_SDRM.py:143)
             loss = neg_ll + anneal * vae_kl + model.get_l2_reg()
             losses.append(loss.detach())
@@ -316,13 +328,24 @@ def train_SDRM(dl, N_ITEMS, VAE_HIDDEN, VAE_LATENT, VAE_BATCH_SIZE, VAE_LR, DIFF
     encoder = training.FrozenEncoder(variational_ae)   # sparse rows -> mu without densifying the batch (train_SDRM.py:323-324)
 
     start_time = time.time()
+    # The VAE is frozen and its eval-mode encode is deterministic (train_SDRM.py:291-294), so mu of EVERY training row is computed
+    # once from the device-resident CSR matrix instead of once per epoch from re-collated host batches; the loader's own batch
+    # sampler still decides which rows form each minibatch.  Any other iterable `dl` takes the generic path.
+    staged = training.stage_loader(dl, dev)
+    mu_all = None
+    if staged is not None:
+        rows_all, batch_sampler = staged
+        mu_all = encoder(rows_all.as_torch_csr())
     for ep in range(DIFF_TRAINING_EPOCHS):
         if verbose:
             print(f"SDRM Epoch: {ep + 1}/{DIFF_TRAINING_EPOCHS}", end="\r")
         diff_optim.param_groups[0]["lr"] = DIFF_LR * (1 - ep / DIFF_TRAINING_EPOCHS)
-        for x, _ in iter(dl):
+        if mu_all is not None:
+            batches = (mu_all[torch.as_tensor(idx, device=dev)] for idx in batch_sampler)
+        else:
+            batches = (encoder(x) for x, _ in iter(dl))
+        for encode_x in batches:
             diff_optim.zero_grad()
-            encode_x = encoder(x)
             loss = stepper.loss(encode_x)
             loss.backward()
             diff_optim.step()

@@ -211,6 +211,137 @@ def denoiser_gemms(net, x, t, passes=3):
                                L, net.n_hidden_layers, int(passes))
 
 
+# --------------------------------------------------------------------------------------------------------------------
+# torch.nn.Linear on the tcgen05 GEMM (MultiVAE++ training step; reference train_SDRM.py:136-150, 210-215)
+# --------------------------------------------------------------------------------------------------------------------
+def _tc_gemm(A, trans_a, B, trans_b, bias, M, N, K, passes, splits):
+    lib = _lib.load()
+    need = lib.sdrm_gemm_workspace_bytes(M, N, K, splits)
+    ws = torch.empty(need, dtype=torch.uint8, device=A.device)
+    C_ = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    rc = lib.sdrm_gemm(_lib.ptr(A), A.stride(0), int(trans_a), _lib.ptr(B), B.stride(0), int(trans_b), _lib.ptr(bias), _lib.ptr(C_),
+                       C_.stride(0), M, N, K, passes, splits, _lib.ptr(ws), need, _lib.stream_ptr())
+    _lib.check(rc, "sdrm_gemm")
+    return C_
+
+
+class TcLinear(torch.autograd.Function):
+    """y = x W^T + b with the forward product and both backward products (dx = dy W, dW = dy^T x) on the hand-written tcgen05
+    GEMM (C ABI `sdrm_gemm`, bf16x3 split operands by default); db is a column sum."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, passes):
+        if x.device.type != "cuda":
+            raise _lib.SdrmError("TcLinear: CUDA tensors required (no CPU fallback)")
+        x_ = x.detach().float()
+        x_ = x_ if x_.stride(-1) == 1 and x_.dim() == 2 else x_.reshape(-1, x.shape[-1]).contiguous()
+        W_ = W.detach().float()
+        W_ = W_ if W_.stride(1) == 1 else W_.contiguous()
+        b_ = b.detach().float().contiguous() if b is not None else None
+        M, K = x_.shape
+        N = W_.shape[0]
+        y = _tc_gemm(x_, False, W_, False, b_, M, N, K, passes, 1)
+        ctx.save_for_backward(x_, W_)
+        ctx.passes = passes
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x_, W_ = ctx.saved_tensors
+        g = g.detach().float()
+        g = g if g.stride(1) == 1 else g.contiguous()
+        M, K = x_.shape
+        N = W_.shape[0]
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _tc_gemm(g, False, W_, True, None, M, K, N, ctx.passes, 1)          # [M, K] = g [M, N] . W [N, K]
+        if ctx.needs_input_grad[1]:
+            gW = _tc_gemm(g, True, x_, True, None, N, K, M, ctx.passes, 0)           # [N, K] = g^T [N, M] . x [M, K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gW, gb, None
+
+
+def tc_linear(x, layer, passes=3):
+    return TcLinear.apply(x, layer.weight, layer.bias, int(passes))
+
+
+def vae_forward_tc(vae, X, passes=3):
+    """VAE.forward (encode + reparameterise + decode + KL, train_SDRM.py:236-256) with the four Linear layers on the tcgen05
+    GEMM; the elementwise pieces (normalise, dropout, tanh, KL, reparameterisation) stay torch ops under autograd.
+    Same RNG draws as VAE.forward: the dropout mask, then randn_like(std)."""
+    h = vae.dropout(torch.nn.functional.normalize(X, p=2, dim=1))
+    h = torch.tanh(tc_linear(h, vae.encoder[0], passes))
+    h = tc_linear(h, vae.encoder[2], passes)
+    mu_q, logvar_q = torch.chunk(h, chunks=2, dim=1)
+    kl = -0.5 * torch.mean(torch.sum(1 + logvar_q - mu_q.pow(2) - logvar_q.exp(), dim=1))
+    z = vae.reparameterize(mu_q, logvar_q)
+    d = torch.tanh(tc_linear(z, vae.decoder[0], passes))
+    return tc_linear(d, vae.decoder[2], passes), kl
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# device-resident CSR staging of the interaction matrix (SURVEY.md 8f-4; reference dataloaders.py:46-79, train_SDRM.py:136, 323)
+# --------------------------------------------------------------------------------------------------------------------
+class DeviceCSR:
+    """The interaction matrix uploaded ONCE as CSR (int64 indptr / indices, fp32 values); minibatches are row-index slices
+    taken on the device.  The reference converts every minibatch from scipy to a torch COO tensor on the host
+    (`torch.LongTensor(tuple of ndarrays)`, dataloaders.py:54), ships it and densifies it."""
+
+    def __init__(self, csr, device):
+        csr = csr.tocsr()
+        self.shape = csr.shape
+        self.host_indptr = csr.indptr.astype("int64")
+        self.indptr = torch.from_numpy(self.host_indptr).to(device)
+        self.indices = torch.from_numpy(csr.indices.astype("int64")).to(device)
+        self.values = torch.from_numpy(csr.data.astype("float32")).to(device)
+        self.device = torch.device(device)
+
+    def as_torch_csr(self):
+        return torch.sparse_csr_tensor(self.indptr, self.indices, self.values, size=self.shape)
+
+    def _gather(self, rows):
+        """positions of the stored entries of `rows` (host int array / list): (row id inside the batch, position in indices)"""
+        import numpy as np
+        rows = np.asarray(rows, dtype=np.int64)
+        lens = self.host_indptr[rows + 1] - self.host_indptr[rows]          # host copy of indptr: no device sync for the sizes
+        total = int(lens.sum())
+        r_dev = torch.from_numpy(rows).to(self.device)
+        lens_dev = torch.from_numpy(lens).to(self.device)
+        row_of = torch.repeat_interleave(torch.arange(len(rows), device=self.device), lens_dev, output_size=total)
+        start_excl = torch.cumsum(lens_dev, 0) - lens_dev
+        pos = self.indptr[r_dev][row_of] + (torch.arange(total, device=self.device) - start_excl[row_of])
+        return row_of, pos, lens_dev
+
+    def dense_rows(self, rows):
+        """dense fp32 [len(rows), I] batch built on the device (duplicates add up, like to_dense() of a COO tensor)"""
+        row_of, pos, _ = self._gather(rows)
+        out = torch.zeros((len(rows), self.shape[1]), dtype=torch.float32, device=self.device)
+        out.index_put_((row_of, self.indices[pos]), self.values[pos], accumulate=True)
+        return out
+
+    def csr_rows(self, rows):
+        row_of, pos, lens_dev = self._gather(rows)
+        indptr = torch.zeros(len(rows) + 1, dtype=torch.int64, device=self.device)
+        indptr[1:] = torch.cumsum(lens_dev, 0)
+        return torch.sparse_csr_tensor(indptr, self.indices[pos], self.values[pos], size=(len(rows), self.shape[1]))
+
+
+def stage_loader(dl, device):
+    """If `dl` is a torch DataLoader over a sdrm_b200.data.SparseDataset driven by a BatchSampler (what main.py builds,
+    main.py:126-135), return (DeviceCSR of the whole dataset, the batch sampler): iterating the sampler yields exactly the
+    index batches that iterating `dl` would have collated, without the per-batch host conversion.  Otherwise None."""
+    ds = getattr(dl, "dataset", None)
+    sampler = getattr(dl, "sampler", None)
+    if ds is None or sampler is None or not hasattr(ds, "get_all_data") or not hasattr(sampler, "batch_size"):
+        return None
+    data, _ = ds.get_all_data()
+    if not hasattr(data, "tocsr"):
+        return None
+    return DeviceCSR(data, device), sampler
+
+
 class ScoreMatchingLoss(torch.autograd.Function):
     """loss = 0.5 (mean((sd-r)^2) + mean((r-sx)^2)) / (1e-8 + var(r)),  r = pred - mu, sd = (psx - sx)/mu_coef^2,
     with means / variance over the GLOBAL batch when `group` is a process group."""

@@ -7,18 +7,19 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _gemm_nt(A, B, bias, passes, splits):
+def _gemm_nt(A, B, bias, passes, splits, trans_a=False, trans_b=False):
+    """C = op(A) op(B)^T; with trans_x the tensor passed is the [K, *] transposed storage."""
     from sdrm_b200 import _lib
     lib = _lib.load()
-    M, K = A.shape
-    N = B.shape[0]
+    M, K = (A.shape[1], A.shape[0]) if trans_a else A.shape
+    N = B.shape[1] if trans_b else B.shape[0]
     C = torch.full((M, N), float("nan"), device="cuda")
-    need = lib.sdrm_gemm_nt_workspace_bytes(M, N, K, splits)
+    need = lib.sdrm_gemm_workspace_bytes(M, N, K, splits)
     ws = torch.empty(need, dtype=torch.uint8, device="cuda")
-    rc = lib.sdrm_gemm_nt(_lib.ptr(A), A.stride(0), _lib.ptr(B), B.stride(0), _lib.ptr(bias), _lib.ptr(C), C.stride(0), M, N, K,
-                          passes, splits, _lib.ptr(ws), need, _lib.stream_ptr())
-    _lib.check(rc, "sdrm_gemm_nt")
-    _lib.check(lib.sdrm_train_check_device_error(_lib.ptr(ws), _lib.stream_ptr()), "sdrm_gemm_nt (device)")
+    rc = lib.sdrm_gemm(_lib.ptr(A), A.stride(0), int(trans_a), _lib.ptr(B), B.stride(0), int(trans_b), _lib.ptr(bias), _lib.ptr(C),
+                       C.stride(0), M, N, K, passes, splits, _lib.ptr(ws), need, _lib.stream_ptr())
+    _lib.check(rc, "sdrm_gemm")
+    _lib.check(lib.sdrm_train_check_device_error(_lib.ptr(ws), _lib.stream_ptr()), "sdrm_gemm (device)")
     return C
 
 
@@ -88,6 +89,18 @@ def _fwd_bwd_report(L, T, nh, B, slopes):
 
 
 # bf16x3 operands carry 16 mantissa bits (hi + bf16(lo)): a product is good to ~1.5e-5 relative, a gradient to ~1e-5 of its terms.
+@pytest.mark.parametrize("ta,tb,splits", [(False, True, 1), (True, True, 0), (True, False, 2), (False, False, 0)])
+def test_gemm_transposed_operands_and_auto_splits(ta, tb, splits):
+    """the three products of a Linear layer: y = x W^T (nt), dx = dy W (B given transposed), dW = dy^T x (both transposed)"""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 333, 217, 1200
+    A = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g)
+    B = torch.randn((K, N) if tb else (N, K), device="cuda", generator=g) / K ** 0.5
+    C = _gemm_nt(A, B, None, 3, splits, ta, tb)
+    ref = (A.double().T if ta else A.double()) @ (B.double() if tb else B.double().T)
+    assert (C.double() - ref).abs().max().item() <= 3e-5 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("L,T,nh,B", [(20, 6, 0, 5), (24, 7, 2, 12), (150, 43, 1, 100), (300, 7, 2, 100), (830, 83, 2, 550),
                                       (950, 178, 4, 700)])
 def test_denoiser_fwd_bwd_matches_autograd_linear_slopes(L, T, nh, B):

@@ -49,6 +49,11 @@ SIGNATURES = {
     "sdrm_gemm_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64, C.c_int]),
     "sdrm_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                             C.c_int, _P, C.c_size_t, _P]),
+    "sdrm_select_state_bytes": (C.c_size_t, []),
+    "sdrm_select_begin": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P]),
+    "sdrm_select_histogram": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P, C.c_int, _P, _P]),
+    "sdrm_select_walk": (C.c_int, [_P, _P, C.c_int, C.c_double, C.c_int, _P]),
+    "sdrm_select_threshold_pack": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, _P, C.c_int, _P, C.c_int64, _P, _P]),
     "sdrm_loss_grad_seeds": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_double, _P, _P, _P, _P, _P, _P]),
 }
 

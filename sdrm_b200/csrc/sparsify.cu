@@ -28,6 +28,21 @@ __device__ __forceinline__ uint32_t score_key(float x) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Device-resident state of one quantile selection (sdrm_select_*): the radix select walks its histograms on the DEVICE, so the
+// three passes, the threshold and the bit-packing are enqueued back to back without a host round trip in between.
+struct SelectState {
+  unsigned long long rem[2];   // rank of the two order statistics np.quantile interpolates between, inside the current prefix
+  unsigned long long nan_count;
+  uint32_t prefix;             // key bits fixed so far (both statistics share them, else `fallback`)
+  uint32_t fallback;           // 1 = the two statistics part ways before the last digit (or the upper one lies outside the
+                               //     last digit's prefix): the caller must take the host-walk path (rare)
+  uint32_t two;                // 1 = two distinct ranks, 0 = a single order statistic
+  uint32_t pad;
+  double threshold;            // the interpolated quantile (NaN if the matrix holds a NaN, like np.quantile)
+  float v0, v1;                // the two order statistics
+};
+static_assert(sizeof(SelectState) == 56, "SelectState layout (mirrored by sdrm_b200/sparsify.py)");
+
 struct MatView {
   const float* x;
   long long rows, ld;
@@ -76,10 +91,13 @@ __device__ __forceinline__ void for_each_score(const MatView& m, F&& f) {
 // One radix-select pass: histogram of the `bits`-wide digit at `shift` over the keys whose top `prefix_bits` bits equal
 // `prefix`; each warp keeps a private shared-memory histogram (no inter-warp conflicts), merged into global memory once.
 __global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint32_t prefix, int prefix_bits, int shift, int bits,
-                                                               unsigned long long* __restrict__ hist) {
+                                                               unsigned long long* __restrict__ hist, SelectState* __restrict__ st) {
   extern __shared__ uint32_t sh[];   // [HIST_WARPS][HIST_BINS]
   for (int i = threadIdx.x; i < HIST_WARPS * HIST_BINS; i += HIST_THREADS) sh[i] = 0;
   __syncthreads();
+  if (st) prefix = st->prefix;       // device-side selection: the prefix was written by select_walk_kernel
+  unsigned int nans = 0;
+  const bool count_nan = st != nullptr && prefix_bits == 0;
   uint32_t* mine = sh + (threadIdx.x >> 5) * HIST_BINS;
   const uint32_t mask = (1u << bits) - 1u;
   const int pshift = 32 - prefix_bits;
@@ -89,6 +107,7 @@ __global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint3
     // skewed (a handful of exponent values), the hardware's in-warp conflict serialisation is 4.7x faster than merging
     // equal bins with match.any first (measured on B200: 2.08 ms vs 9.69 ms for 10 GB).
     if (prefix_bits == 0 || (k >> pshift) == prefix) atomicAdd(mine + ((k >> shift) & mask), 1u);
+    if (count_nan && v != v) ++nans;   // np.quantile returns NaN as soon as one score is NaN
   };
   for_each_score(m, add);
   __syncthreads();
@@ -98,6 +117,96 @@ __global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint3
     for (int w = 0; w < HIST_WARPS; ++w) s += sh[w * HIST_BINS + b];
     if (s) atomicAdd(hist + b, s);
   }
+  if (count_nan) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nans += __shfl_xor_sync(0xffffffffu, nans, o);
+    if ((threadIdx.x & 31) == 0 && nans) atomicAdd(&st->nan_count, static_cast<unsigned long long>(nans));
+  }
+}
+
+__global__ void select_init_kernel(SelectState* st, unsigned long long r0, unsigned long long r1) {
+  st->rem[0] = r0; st->rem[1] = r1; st->nan_count = 0; st->prefix = 0; st->fallback = 0; st->two = (r1 != r0) ? 1u : 0u; st->pad = 0;
+  st->threshold = 0.0; st->v0 = st->v1 = 0.0f;
+}
+
+__device__ __forceinline__ float key_float(uint32_t key) {
+  const uint32_t u = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+  return __uint_as_float(u);
+}
+
+// One block walks one (all-reduced) histogram: finds the digit of the lower order statistic, checks that the upper one (rank
+// + 1) shares it, narrows the prefix; behind the LAST digit it rebuilds the two floats and interpolates with NumPy's rule
+// (numpy/lib/_function_base_impl.py _lerp; since NumPy 2.0 gamma is float32 for float32 data, before it was float64).
+__global__ void __launch_bounds__(1024) select_walk_kernel(const unsigned long long* __restrict__ hist, SelectState* st, int bits, int last,
+                                                           double gamma, int gamma_f32) {
+  __shared__ unsigned long long cum[HIST_BINS];
+  __shared__ unsigned long long part[32];
+  const int n = 1 << bits;
+  const int t = threadIdx.x;
+  // inclusive scan of up to 2048 bins with 1024 threads (two bins per thread)
+  const unsigned long long a = (2 * t < n) ? hist[2 * t] : 0ull, b = (2 * t + 1 < n) ? hist[2 * t + 1] : 0ull;
+  unsigned long long v = a + b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, v, o);
+    if ((t & 31) >= o) v += u;
+  }
+  if ((t & 31) == 31) part[t >> 5] = v;
+  __syncthreads();
+  if (t < 32) {
+    unsigned long long p = part[t];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long u = __shfl_up_sync(0xffffffffu, p, o);
+      if (t >= o) p += u;
+    }
+    part[t] = p;
+  }
+  __syncthreads();
+  const unsigned long long base = (t >= 32) ? part[(t >> 5) - 1] : 0ull;
+  if (2 * t < n) cum[2 * t] = base + v - b;
+  if (2 * t + 1 < n) cum[2 * t + 1] = base + v;
+  __syncthreads();
+  if (t == 0) {
+    const unsigned long long r0 = st->rem[0];
+    // first bin whose inclusive count exceeds r0 (binary search)
+    int lo = 0, hi = n - 1;
+    if (r0 >= cum[n - 1]) { st->fallback = 1; return; }   // rank beyond the number of scores: let the host path raise
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cum[mid] > r0) hi = mid; else lo = mid + 1; }
+    const int b0 = lo;
+    const unsigned long long before = b0 ? cum[b0 - 1] : 0ull;
+    int b1 = b0;
+    if (st->two && r0 + 1 >= cum[b0]) {
+      // the upper statistic is the first score of a later bin
+      b1 = b0 + 1;
+      while (b1 < n && cum[b1] == cum[b0]) ++b1;
+      if (!last || b1 >= n) st->fallback = 1;
+    }
+    const uint32_t p0 = (st->prefix << bits) | static_cast<uint32_t>(b0);
+    if (!last) {
+      st->prefix = p0;
+      st->rem[0] = r0 - before;
+    } else {
+      const uint32_t p1 = (st->prefix << bits) | static_cast<uint32_t>(b1 < n ? b1 : b0);
+      const float x0 = key_float(p0), x1 = st->two ? key_float(p1) : x0;
+      st->v0 = x0; st->v1 = x1;
+      double thr;
+      if (gamma_f32) {   // float32 arithmetic without contraction, exactly _lerp on np.float32 scalars
+        const float g = static_cast<float>(gamma);
+        const float diff = __fsub_rn(x1, x0);
+        float o = __fadd_rn(x0, __fmul_rn(diff, g));
+        if (g >= 0.5f) o = __fsub_rn(x1, __fmul_rn(diff, __fsub_rn(1.0f, g)));
+        thr = static_cast<double>(o);
+      } else {           // NumPy < 2.0: gamma is float64, the float32 difference is promoted
+        const double diff = static_cast<double>(__fsub_rn(x1, x0));
+        double o = __dadd_rn(static_cast<double>(x0), __dmul_rn(diff, gamma));
+        if (gamma >= 0.5) o = __dsub_rn(static_cast<double>(x1), __dmul_rn(diff, __dsub_rn(1.0, gamma)));
+        thr = o;
+      }
+      if (st->nan_count) thr = __longlong_as_double(0x7ff8000000000000ll);
+      st->threshold = thr;
+    }
+  }
 }
 
 // bits[row][w] bit j = (score[row][32 w + j] >= thr)  (mode 0)  or  <= thr (mode 1).  A warp walks whole rows: every lane
@@ -105,8 +214,15 @@ __global__ void __launch_bounds__(HIST_THREADS) key_hist_kernel(MatView m, uint3
 // assemble the four 32-bit words of the 128 columns.
 template <int MODE>
 __global__ void __launch_bounds__(256) threshold_pack_kernel(MatView m, float thr, uint32_t* __restrict__ bits,
-                                                             long long words_per_row, unsigned long long* __restrict__ count) {
+                                                             long long words_per_row, unsigned long long* __restrict__ count,
+                                                             const SelectState* __restrict__ st) {
   const int lane = threadIdx.x & 31;
+  if (st) {   // threshold selected on the device: same double -> float32 predicate conversion as the host entry
+    const double td = st->threshold;
+    thr = static_cast<float>(td);
+    if (MODE == 0 && static_cast<double>(thr) < td) thr = nextafterf(thr, INFINITY);
+    if (MODE == 1 && static_cast<double>(thr) > td) thr = nextafterf(thr, -INFINITY);
+  }
   const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long n_warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
   const bool vec = ((m.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(m.x) & 15) == 0);
@@ -205,7 +321,60 @@ int sdrm_key_histogram(const float* d_scores, int64_t rows, int n_cols, int64_t 
   }
   MatView m{d_scores, rows, ld, n_cols};
   const int grid = grid_for(rows * static_cast<long long>(n_cols), HIST_THREADS, 64, 3);
-  key_hist_kernel<<<grid, HIST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(m, prefix, prefix_bits, shift, bits, d_hist);
+  key_hist_kernel<<<grid, HIST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(m, prefix, prefix_bits, shift, bits, d_hist, nullptr);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+static const int kDigitBits[3] = {11, 11, 10}, kDigitShift[3] = {21, 10, 0};
+
+size_t sdrm_select_state_bytes(void) { return sizeof(SelectState); }
+
+int sdrm_select_begin(void* d_state, uint64_t rank_lo, uint64_t rank_hi, void* stream) {
+  if (!d_state || rank_hi < rank_lo || rank_hi > rank_lo + 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_begin: state / ranks (rank_hi must be rank_lo or rank_lo + 1)");
+  select_init_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<SelectState*>(d_state), rank_lo, rank_hi);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_select_histogram(const float* d_scores, int64_t rows, int n_cols, int64_t ld, void* d_state, int digit,
+                          unsigned long long* d_hist, void* stream) {
+  if (!d_scores || !d_hist || !d_state) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_histogram: null pointer");
+  if (rows < 0 || n_cols <= 0 || ld < n_cols || digit < 0 || digit > 2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_histogram: bad shape / digit");
+  if (rows == 0) return SDRM_OK;
+  static bool attr_done = false;
+  const int smem = HIST_WARPS * HIST_BINS * static_cast<int>(sizeof(uint32_t));
+  if (!attr_done) {
+    SDRM_CUDA(cudaFuncSetAttribute(key_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  MatView m{d_scores, rows, ld, n_cols};
+  const int grid = grid_for(rows * static_cast<long long>(n_cols), HIST_THREADS, 64, 3);
+  key_hist_kernel<<<grid, HIST_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(m, 0u, 32 - kDigitBits[digit] - kDigitShift[digit], kDigitShift[digit],
+                                                                                   kDigitBits[digit], d_hist, static_cast<SelectState*>(d_state));
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_select_walk(const unsigned long long* d_hist, void* d_state, int digit, double gamma, int gamma_is_f32, void* stream) {
+  if (!d_hist || !d_state || digit < 0 || digit > 2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_walk: bad argument");
+  select_walk_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(d_hist, static_cast<SelectState*>(d_state), kDigitBits[digit], digit == 2, gamma,
+                                                                        gamma_is_f32);
+  SDRM_CUDA(cudaGetLastError());
+  return SDRM_OK;
+}
+
+int sdrm_select_threshold_pack(const float* d_scores, int64_t rows, int n_cols, int64_t ld, const void* d_state, int mode,
+                               uint32_t* d_bits, int64_t words_per_row, unsigned long long* d_count, void* stream) {
+  if (!d_scores || !d_bits || !d_state) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_threshold_pack: null pointer");
+  if (rows < 0 || n_cols <= 0 || ld < n_cols || words_per_row < (n_cols + 31) / 32 || (mode != 0 && mode != 1))
+    return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_select_threshold_pack: bad shape / mode");
+  if (rows == 0) return SDRM_OK;
+  MatView m{d_scores, rows, ld, n_cols};
+  const int grid = grid_for(rows * 32, 256, 1, 8);
+  const SelectState* st = static_cast<const SelectState*>(d_state);
+  if (mode == 0) threshold_pack_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, 0.0f, d_bits, words_per_row, d_count, st);
+  else threshold_pack_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, 0.0f, d_bits, words_per_row, d_count, st);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
 }
@@ -223,8 +392,8 @@ int sdrm_threshold_pack(const float* d_scores, int64_t rows, int n_cols, int64_t
   if (mode == 0 && static_cast<double>(tf) < threshold) tf = nextafterf(tf, INFINITY);
   if (mode == 1 && static_cast<double>(tf) > threshold) tf = nextafterf(tf, -INFINITY);
   const int grid = grid_for(rows * 32, 256, 1, 8);   // one warp per row until the wave is full
-  if (mode == 0) threshold_pack_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count);
-  else threshold_pack_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count);
+  if (mode == 0) threshold_pack_kernel<0><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count, nullptr);
+  else threshold_pack_kernel<1><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(m, tf, d_bits, words_per_row, d_count, nullptr);
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
 }

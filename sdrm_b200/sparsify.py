@@ -144,14 +144,26 @@ def global_count(scores, group=None):
     return n
 
 
-def quantile_device(scores, q, group=None):
-    """np.quantile(S.flatten(), q) for a float32 CUDA matrix (row-sharded over `group` if given), bit-identical to NumPy."""
+def quantile_host_walk(scores, q, group=None):
+    """The first implementation: histograms copied to the host between the passes and walked with NumPy (also the fallback of
+    the device walk).  NaN scores are not looked for here (the device walk counts them; quantile_device handles that)."""
     _check(scores)
     n_total = global_count(scores, group)
     prev_i, nxt_i, gamma = quantile_plan(n_total, q, np.float32)
     ranks = [prev_i] if nxt_i == prev_i else [prev_i, nxt_i]
     vals = select_ranks(device_histogram_fn(scores, group), ranks)
     return lerp(vals[0], vals[-1], gamma)
+
+
+def quantile_device(scores, q, group=None):
+    """np.quantile(S.flatten(), q) for a float32 CUDA matrix (row-sharded over `group` if given), bit-identical to NumPy
+    (NaN as soon as one score is NaN)."""
+    _check(scores)
+    state, g32 = _select_enqueue(scores, q, group)
+    thr, fallback, nans = _read_state(state, g32)
+    if nans:
+        return np.float32(np.nan)
+    return quantile_host_walk(scores, q, group) if fallback else thr
 
 
 class PackedMatrix:
@@ -185,12 +197,70 @@ def threshold_pack(scores, threshold, lower=False):
     return PackedMatrix(bits, n_cols, threshold, count)
 
 
-def equal_sparsity_device(scores, sparsity, group=None, lower=False):
+def _select_enqueue(scores, q, group):
+    """Enqueue the device-side quantile selection (C ABI sdrm_select_*): three histogram passes with a one-block walk kernel
+    between them (and one all-reduce of 2048 bins per pass when the rows are sharded); nothing is read back here."""
+    lib = _lib.load()
+    dist = _world(group)
+    rows, n_cols = scores.shape
+    n_total = global_count(scores, group)
+    prev_i, nxt_i, gamma = quantile_plan(n_total, q, np.float32)
+    dev = scores.device
+    state = torch.zeros(lib.sdrm_select_state_bytes(), dtype=torch.uint8, device=dev)
+    hists = torch.zeros((3, 2048), dtype=torch.int64, device=dev)
+    st = _lib.stream_ptr()
+    ld = scores.stride(0) if rows else n_cols
+    _lib.check(lib.sdrm_select_begin(_lib.ptr(state), prev_i, nxt_i, st), "sdrm_select_begin")
+    g32 = 1 if np.asarray(gamma).dtype == np.float32 else 0
+    for d in range(3):
+        _lib.check(lib.sdrm_select_histogram(_lib.ptr(scores), rows, n_cols, ld, _lib.ptr(state), d, _lib.ptr(hists[d]), st),
+                   "sdrm_select_histogram")
+        if dist is not None:
+            dist.all_reduce(hists[d], group=group)
+            if d == 0:      # the NaN count of the other ranks (bytes 16..24 of the state)
+                dist.all_reduce(state[16:24].view(torch.int64), group=group)
+        _lib.check(lib.sdrm_select_walk(_lib.ptr(hists[d]), _lib.ptr(state), d, float(gamma), g32, st), "sdrm_select_walk")
+    return state, g32
+
+
+def _read_state(state, g32):
+    raw = state.cpu().numpy()          # the only synchronisation of the selection
+    thr = raw[40:48].view(np.float64)[0]
+    return (np.float32(thr) if g32 else np.float64(thr)), int(raw[28:32].view(np.uint32)[0]), int(raw[16:24].view(np.uint64)[0])
+
+
+def _select_pack_device(scores, q, group, lower):
+    """Quantile selection + bit packing enqueued back to back: ONE host read (the 56-byte state) at the end instead of a
+    device->host histogram copy and a host walk per pass.  Returns None when the device walk flagged the rare case it does not
+    handle (the two order statistics fall into different digit bins before the last digit): the caller takes the host walk."""
+    lib = _lib.load()
+    rows, n_cols = scores.shape
+    state, g32 = _select_enqueue(scores, q, group)
+    wpr = (n_cols + 31) // 32
+    bits = torch.empty((rows, wpr), dtype=torch.int32, device=scores.device)
+    count = torch.zeros(1, dtype=torch.int64, device=scores.device)
+    _lib.check(lib.sdrm_select_threshold_pack(_lib.ptr(scores), rows, n_cols, scores.stride(0) if rows else n_cols, _lib.ptr(state),
+                                              1 if lower else 0, _lib.ptr(bits), wpr, _lib.ptr(count), _lib.stream_ptr()),
+               "sdrm_select_threshold_pack")
+    thr, fallback, nans = _read_state(state, g32)
+    if fallback and not nans:
+        return None
+    return PackedMatrix(bits, n_cols, thr, count)
+
+
+def equal_sparsity_device(scores, sparsity, group=None, lower=False, host_walk=False):
     """The reference's equal-sparsity binarisation (main.py:177-185) without leaving the GPU.
 
     lower=False: S >= np.quantile(S.flatten(), sparsity);  lower=True: S <= np.quantile(S.flatten(), 1 - sparsity)
     (main.py:259-262).  With `group`, `scores` is this rank's row shard and the threshold is the GLOBAL quantile.
+    A NaN score makes the threshold NaN (and every bit 0), like np.quantile.  host_walk=True forces the first implementation
+    (histograms copied to the host between the passes), which is also the fallback of the device walk.
     """
+    _check(scores)
     q = (1 - sparsity) if lower else sparsity
-    thr = quantile_device(scores, q, group)
+    if not host_walk and scores.shape[0] > 0:
+        pm = _select_pack_device(scores, q, group, lower)
+        if pm is not None:
+            return pm
+    thr = quantile_host_walk(scores, q, group) if host_walk else quantile_device(scores, q, group)
     return threshold_pack(scores, thr, lower=lower)

@@ -9,7 +9,7 @@ from helpers import max_scaled_err, modules_from_golden, random_modules, rel_fro
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-3      # north_star: synthetic rows within 1e-3 relative (bf16 operands, fp32 accumulate) -> rel-Frobenius
-TOL_MAX = 5e-3  # sanity bound on the worst single element, |d| / max(1, |ref|)
+TOL_MAX = 2e-3  # worst single element, |d| / max(1, |ref|): measured 4.9e-5 ... 1.02e-3 at the full chain lengths of cfg 1-3 and cfg 5 (r02)
 
 
 def _engine(diff, vae, T, nd):
@@ -184,3 +184,89 @@ def test_headline_config_rows_match_oracle_at_full_scale():
         got = out[start:start + rows].cpu()
         assert rel_fro(got, ref) < TOL, (start, rel_fro(got, ref))
         assert max_scaled_err(got, ref) < TOL_MAX
+
+
+# BASELINE.json configs 1-3 at their REAL sizes and FULL chain lengths (T = 83 / 78 / 93); the CPU oracle runs the whole chain on
+# 12-row slices (rows depend only on (seed, global row id), so a slice of the launch equals a launch of the slice).
+FULL_T_CONFIGS = {
+    "cfg1": (843, 1008, 930, 830, 83, 2, 1.0),
+    "cfg2": (5429, 3125, 490, 340, 78, 1, 1.0),
+    "cfg3": (9558, 8582, 40, 40, 93, 5, 1.0),
+}
+
+
+@pytest.mark.parametrize("cfg", sorted(FULL_T_CONFIGS))
+def test_dataset_configs_full_chain_length(cfg):
+    from oracle import philox_ref
+    from oracle import sdrm_oracle as orc
+    n, I, H, L, T, nh, nd = FULL_T_CONFIGS[cfg]
+    diff, vae = random_modules(I, H, L, T, nh, seed=21, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    seed, row_offset = 0xABCDEF0123, 77
+    out = eng.sample(n, row_offset=row_offset, seed=seed, check=True)
+    assert torch.isfinite(out).all()
+    dsd, vsd = state_dicts(diff, vae)
+    worst_fro, worst_el = 0.0, 0.0
+    for start in (0, (n // 2) // 128 * 128 + 19, n - 12):     # first tile, a middle tile, the ragged last tile
+        xT, z, keep = philox_ref.sampler_noise(seed, row_offset + start, 12, L, T)
+        ref = orc.sample_full(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep))
+        got = out[start:start + 12].cpu()
+        worst_fro = max(worst_fro, rel_fro(got, ref))
+        worst_el = max(worst_el, max_scaled_err(got, ref))
+    print(f"{cfg} full T={T}: logits rel-Frobenius {worst_fro:.2e}, worst element |d|/max(1,|ref|) {worst_el:.2e}")
+    assert worst_fro < TOL and worst_el < TOL_MAX
+
+
+def test_random_mode_at_cfg1_shape_through_the_public_call():
+    """sample_ddpm(timesteps='random') at the ml-100k shape (843 users, T = 83): t_j ~ np.random.randint(1, T) like the reference
+    (train_SDRM.py:42); the call sorts the rows by chain length internally and must return them in logical order."""
+    from oracle import philox_ref
+    from oracle import sdrm_oracle as orc
+    from sdrm_b200.train_SDRM import sample_ddpm
+    n, I, H, L, T, nh, nd = FULL_T_CONFIGS["cfg1"]
+    diff, vae = random_modules(I, H, L, T, nh, seed=22, device="cuda")
+    np.random.seed(31)
+    t_np = np.random.randint(1, T, size=n)             # the draw the call makes itself ...
+    np.random.seed(31)                                  # ... replayed
+    out = sample_ddpm(n, diff, vae, L, nd, timesteps="random", n_timesteps=T, seed=4242)
+    assert out.shape == (n, I) and torch.isfinite(out).all()
+    dsd, vsd = state_dicts(diff, vae)
+    for start in (0, 400, n - 16):
+        xT, z, keep = philox_ref.sampler_noise(4242, start, 16, L, T)
+        ref = orc.sample_random(dsd, vsd, T, nd, torch.from_numpy(xT), torch.from_numpy(z), torch.from_numpy(keep), t_np[start:start + 16])
+        got = out[start:start + 16].cpu()
+        assert rel_fro(got, ref) < TOL, (start, rel_fro(got, ref))
+        assert max_scaled_err(got, ref) < TOL_MAX
+
+
+def test_packed_weights_follow_in_place_data_edits():
+    """an edit through `.data` bumps no version counter; the default call re-packs, so it must see the new weights,
+    and `reuse_packed=True` must be the only way to keep the old images."""
+    from sdrm_b200.train_SDRM import sample_ddpm
+    n, I, H, L, T, nh, nd = 200, 150, 64, 48, 5, 1, 1.0
+    diff, vae = random_modules(I, H, L, T, nh, seed=2, device="cuda")
+    a = sample_ddpm(n, diff, vae, L, nd, n_timesteps=T, seed=9).clone()
+    diff.dnn[0].weight.data.mul_(0.5)                       # no _version bump
+    vae.decoder[2].bias.data.add_(1.0)
+    stale = sample_ddpm(n, diff, vae, L, nd, n_timesteps=T, seed=9, reuse_packed=True).clone()
+    fresh = sample_ddpm(n, diff, vae, L, nd, n_timesteps=T, seed=9).clone()
+    assert torch.equal(stale, a)                            # opted-in reuse keeps the old images (documented)
+    assert not torch.equal(fresh, a)
+    diff2, vae2 = random_modules(I, H, L, T, nh, seed=2, device="cuda")
+    diff2.dnn[0].weight.data.mul_(0.5)
+    vae2.decoder[2].bias.data.add_(1.0)
+    assert torch.equal(fresh, sample_ddpm(n, diff2, vae2, L, nd, n_timesteps=T, seed=9))
+
+
+def test_t_start_out_of_range_is_clamped():
+    n, I, H, L, T, nh, nd = 130, 60, 32, 24, 6, 1, 1.0
+    diff, vae = random_modules(I, H, L, T, nh, seed=4, device="cuda")
+    eng = _engine(diff, vae, T, nd)
+    t = torch.full((n,), T, dtype=torch.int32)
+    ref = eng.sample(n, t_start=t.cuda(), seed=5, check=True).clone()
+    bad = t.clone().cuda()
+    bad[::3] = T + 1000                                     # device tensor: the host cannot validate it; the kernel clamps to T
+    out = eng.sample(n, t_start=bad, seed=5, check=True)
+    assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        eng.sample(n, t_start=torch.full((n,), T + 1, dtype=torch.int32), seed=5)   # host tensor: validated

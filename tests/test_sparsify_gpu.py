@@ -37,6 +37,34 @@ def test_equal_sparsity_matches_reference_lines(name, a, sparsity):
     assert got == ref or (np.isnan(got) and np.isnan(ref))
 
 
+def test_device_walk_fallback_nan_and_host_walk_agree():
+    """(a) the two order statistics in different top-digit bins (the device walk flags it and the host walk takes over);
+    (b) NaN scores make the threshold NaN and every bit 0 like np.quantile; (c) host_walk=True gives the same bits."""
+    from sdrm_b200.sparsify import equal_sparsity_device, quantile_device
+    a = np.concatenate([np.full(50, 1.0, np.float32), np.full(50, 1.0e20, np.float32)]).reshape(10, 10)   # ranks 49 | 50 straddle
+    x = torch.from_numpy(a).cuda()
+    q = 49.5 / 99
+    ref = np.quantile(a.flatten(), np.float32(q))
+    assert quantile_device(x, q) == np.quantile(a.flatten(), q)
+    ref_bin, ref_thr = so.equal_sparsity_reference(a, q)
+    pm = equal_sparsity_device(x, q)
+    assert pm.threshold == ref_thr and np.array_equal(pm.numpy(int), ref_bin)
+    rng = np.random.RandomState(9)
+    b = rng.randn(300, 500).astype(np.float32)
+    xb = torch.from_numpy(b).cuda()
+    for sp_ in (0.3, 0.977):
+        p1, p2 = equal_sparsity_device(xb, sp_), equal_sparsity_device(xb, sp_, host_walk=True)
+        assert p1.threshold == p2.threshold and torch.equal(p1.bits, p2.bits)
+    b[17, 33] = np.nan
+    b[200, 1] = -np.nan
+    xn = torch.from_numpy(b).cuda()
+    with np.errstate(invalid="ignore"):
+        refq = np.quantile(b.flatten(), 0.9)
+    assert np.isnan(refq) and np.isnan(quantile_device(xn, 0.9))
+    pn = equal_sparsity_device(xn, 0.9)
+    assert np.isnan(pn.threshold) and int(pn.ones.item()) == 0 and not pn.numpy(int).any()
+
+
 def test_strided_view_and_histogram_digits():
     """ld > n_cols (a column slice of a wider tensor) and the raw digit histograms against the NumPy stand-in."""
     from sdrm_b200.sparsify import device_histogram_fn, quantile_device

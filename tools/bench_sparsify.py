@@ -38,4 +38,4 @@ import time
 torch.cuda.synchronize(); t0 = time.perf_counter(); pm = equal_sparsity_device(x, 0.99); torch.cuda.synchronize(); t1 = time.perf_counter()
 for k_, (ms, gbs) in res.items():
     print(f"K4 {k_:32s} {ms:8.3f} ms  {gbs:8.1f} GB/s  {gbs / peak:5.2f} of measured HBM peak ({peak} GB/s)")
-print(f"K4 equal_sparsity_device end to end ({rows}x{cols}, incl. host walks): {(t1 - t0) * 1e3:.1f} ms, ones fraction {int(pm.ones) / x.numel():.6f}")
+print(f"K4 equal_sparsity_device end to end ({rows}x{cols}, device walk, one state read): {(t1 - t0) * 1e3:.1f} ms, ones fraction {int(pm.ones) / x.numel():.6f}")

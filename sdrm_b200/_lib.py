@@ -58,7 +58,7 @@ SIGNATURES = {
 }
 
 
-OPT_CLUSTER, OPT_SUBTILES, OPT_GRID_LIMIT, OPT_NO_DISCARD, OPT_DEBUG_FLAGS, OPT_TRACE_BUFFER = 1, 2, 3, 4, 100, 101   # enum sdrm_option
+OPT_CLUSTER, OPT_SUBTILES, OPT_GRID_LIMIT, OPT_NO_DISCARD, OPT_ENGINE, OPT_DEBUG_FLAGS, OPT_TRACE_BUFFER = 1, 2, 3, 4, 5, 100, 101   # enum sdrm_option
 
 
 class SdrmError(RuntimeError):

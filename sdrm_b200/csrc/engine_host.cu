@@ -13,6 +13,7 @@
 #include "layer_engine.cuh"
 #include "layer_engine_kernel.cuh"
 #include "ptx_sm100.cuh"
+#include "small_chain_kernel.cuh"
 
 namespace sdrm {
 
@@ -148,6 +149,26 @@ __global__ void bias_table_kernel(const float* __restrict__ We, const float* __r
   }
 }
 
+// K6 images: W fp32 [N, ldw] (columns col_off .. col_off + K) -> zero-padded bf16 hi (and lo) [rows_pad][SMALL_KP]
+__global__ void pack_small_weight_kernel(const float* __restrict__ W, int N, int K, long long ldw, int col_off, int rows_pad,
+                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = static_cast<long long>(rows_pad) * SMALL_KP;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total; idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx / SMALL_KP), k = static_cast<int>(idx - static_cast<long long>(r) * SMALL_KP);
+    const float v = (r < N && k < K) ? W[r * ldw + col_off + k] : 0.0f;
+    const float h = bf16_round(v);
+    hi[idx] = __float2bfloat16_rn(h);
+    if (lo) lo[idx] = __float2bfloat16_rn(v - h);
+  }
+}
+// rows of `cols` floats (pitch src_ld) -> rows of 64 zero-padded floats
+__global__ void pad_rows64_kernel(const float* __restrict__ src, long long src_ld, int cols, int rows, float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 64) return;
+  const int r = i >> 6, c = i & 63;
+  dst[i] = (src != nullptr && c < cols) ? src[r * src_ld + c] : 0.0f;
+}
+
 // coef[i] = {(1-a_i)/sqrt(1-ab_i), 1/sqrt(a_i), sqrt(b_i)*nd (0 at i=1), 0}  (train_SDRM.py:20-25,56)
 __global__ void coef_kernel(const float* __restrict__ sched, int T, float nd, float* __restrict__ coef) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -191,6 +212,14 @@ struct sdrm_handle {
   Geom g0, gh, go;
   uint8_t *w0 = nullptr, *wh = nullptr, *wo = nullptr;
   float *bias0 = nullptr, *bh = nullptr, *bo = nullptr, *slopes = nullptr, *coef = nullptr;
+  // K6 (small denoisers, small_chain_kernel.cuh): zero-padded bf16 images and 64-wide bias rows, packed when every width <= 64
+  bool small_den = false, small_dec = false;
+  __nv_bfloat16 *s_den = nullptr;   // w0 | wh | wo, each [64][SMALL_KP]
+  __nv_bfloat16 *s_dec1 = nullptr;  // w1 hi | w1 lo
+  __nv_bfloat16 *s_dec2 = nullptr;  // w2 hi | w2 lo, each [I rounded up to 64][SMALL_KP]
+  float *s_bias = nullptr;          // bias0 [T+1][64] | bh [64] | bo [64]
+  float *s_b1 = nullptr;            // b1 [64] | b2 [I rounded up to 64]
+  int engine_choice = 0;            // SDRM_OPT_ENGINE: 0 automatic, 1 tcgen05 layer engine, 2 small-chain kernel
   // decoder
   bool have_dec = false;
   int H = 0, I = 0;
@@ -202,12 +231,16 @@ struct sdrm_handle {
 static void free_den(sdrm_handle* h) {
   cudaFree(h->w0); cudaFree(h->wh); cudaFree(h->wo);
   cudaFree(h->bias0); cudaFree(h->bh); cudaFree(h->bo); cudaFree(h->slopes); cudaFree(h->coef);
+  cudaFree(h->s_den); cudaFree(h->s_bias);
+  h->s_den = nullptr; h->s_bias = nullptr; h->small_den = false;
   h->w0 = h->wh = h->wo = nullptr;
   h->bias0 = h->bh = h->bo = h->slopes = h->coef = nullptr;
   h->have_den = false;
 }
 static void free_dec(sdrm_handle* h) {
   cudaFree(h->w1); cudaFree(h->w2); cudaFree(h->b1); cudaFree(h->b2);
+  cudaFree(h->s_dec1); cudaFree(h->s_dec2); cudaFree(h->s_b1);
+  h->s_dec1 = h->s_dec2 = nullptr; h->s_b1 = nullptr; h->small_dec = false;
   h->w1 = h->w2 = nullptr;
   h->b1 = h->b2 = nullptr;
   h->have_dec = false;
@@ -421,6 +454,23 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
   if (nh > 0) SDRM_CUDA(cudaMemcpyAsync(h->slopes + 1, d_ah, sizeof(float), cudaMemcpyDeviceToDevice, st));
   coef_kernel<<<(T + 1 + 127) / 128, 128, 0, st>>>(d_sched, T, noise_divider, h->coef);
   SDRM_CUDA(cudaGetLastError());
+  if (L <= SMALL_MAX && D <= SMALL_MAX) {   // K6 images
+    const size_t img = static_cast<size_t>(64) * SMALL_KP;
+    if (!h->s_den) {
+      SDRM_CUDA(cudaMalloc(&h->s_den, 3 * img * sizeof(__nv_bfloat16)));
+      SDRM_CUDA(cudaMalloc(&h->s_bias, sizeof(float) * 64 * (T + 3)));
+    }
+    pack_small_weight_kernel<<<18, 256, 0, st>>>(d_W0, D, L, L + T, 0, 64, h->s_den, nullptr);
+    pack_small_weight_kernel<<<18, 256, 0, st>>>(nh > 0 ? d_Wh : d_Wo, nh > 0 ? D : 0, nh > 0 ? D : 0, D, 0, 64, h->s_den + img, nullptr);
+    pack_small_weight_kernel<<<18, 256, 0, st>>>(d_Wo, L, D, D, 0, 64, h->s_den + 2 * img, nullptr);
+    pad_rows64_kernel<<<(64 * (T + 1) + 255) / 256, 256, 0, st>>>(h->bias0, h->g0.Np, D, T + 1, h->s_bias);
+    pad_rows64_kernel<<<1, 64, 0, st>>>(nh > 0 ? d_bh : nullptr, 0, D, 1, h->s_bias + 64 * (T + 1));
+    pad_rows64_kernel<<<1, 64, 0, st>>>(d_bo, 0, L, 1, h->s_bias + 64 * (T + 2));
+    SDRM_CUDA(cudaGetLastError());
+    h->small_den = true;
+  } else {
+    h->small_den = false;
+  }
   h->have_den = true;
   return SDRM_OK;
 }
@@ -448,6 +498,24 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
   pad_bias_kernel<<<(h->g1.Np + 255) / 256, 256, 0, st>>>(d_b1, H, h->b1, h->g1.Np);
   pad_bias_kernel<<<(h->g2.Np + 255) / 256, 256, 0, st>>>(d_b2, I, h->b2, h->g2.Np);
   SDRM_CUDA(cudaGetLastError());
+  if (L <= SMALL_MAX && H <= SMALL_MAX) {   // K6 images
+    const size_t img = static_cast<size_t>(64) * SMALL_KP;
+    const int I_pad = (I + 63) / 64 * 64;
+    const size_t img2 = static_cast<size_t>(I_pad) * SMALL_KP;
+    if (!h->s_dec1) {
+      SDRM_CUDA(cudaMalloc(&h->s_dec1, 2 * img * sizeof(__nv_bfloat16)));
+      SDRM_CUDA(cudaMalloc(&h->s_dec2, 2 * img2 * sizeof(__nv_bfloat16)));
+      SDRM_CUDA(cudaMalloc(&h->s_b1, sizeof(float) * (64 + I_pad)));
+    }
+    pack_small_weight_kernel<<<18, 256, 0, st>>>(d_W1, H, L, L, 0, 64, h->s_dec1, h->s_dec1 + img);
+    pack_small_weight_kernel<<<static_cast<int>(std::min<size_t>((img2 + 255) / 256, 2048)), 256, 0, st>>>(d_W2, I, H, H, 0, I_pad, h->s_dec2, h->s_dec2 + img2);
+    pad_rows64_kernel<<<1, 64, 0, st>>>(d_b1, 0, H, 1, h->s_b1);
+    pad_bias_kernel<<<(I_pad + 255) / 256, 256, 0, st>>>(d_b2, I, h->s_b1 + 64, I_pad);
+    SDRM_CUDA(cudaGetLastError());
+    h->small_dec = true;
+  } else {
+    h->small_dec = false;
+  }
   h->have_dec = true;
   return SDRM_OK;
 }
@@ -501,6 +569,43 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   if (!d_workspace) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_sample: null workspace");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   SDRM_CUDA(cudaSetDevice(h->device));
+  // ---- small denoisers (every width <= 64): the register / shared-memory resident chain (K6) instead of the tcgen05 engine
+  const bool small_ok = h->small_den && h->small_dec && h->D <= SMALL_MAX && h->H <= SMALL_MAX;
+  if (h->engine_choice == 2 && !small_ok) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_sample: the small-chain kernel needs every width <= 64");
+  if (small_ok && h->engine_choice != 1) {
+    SmallParams S;
+    memset(&S, 0, sizeof S);
+    const size_t img = static_cast<size_t>(64) * SMALL_KP;
+    const size_t img2 = static_cast<size_t>((h->I + 63) / 64 * 64) * SMALL_KP;
+    S.w0 = h->s_den; S.wh = h->s_den + img; S.wo = h->s_den + 2 * img;
+    S.w1_hi = h->s_dec1; S.w1_lo = h->s_dec1 + img;
+    S.w2_hi = h->s_dec2; S.w2_lo = h->s_dec2 + img2;
+    S.bias0 = h->s_bias; S.bias0_ld = 64;
+    S.bh = h->s_bias + 64 * (h->T + 1); S.bo = h->s_bias + 64 * (h->T + 2); S.b1 = h->s_b1; S.b2 = h->s_b1 + 64;
+    S.slopes = h->slopes; S.coef = h->coef;
+    S.T = h->T; S.L = h->L; S.H = h->H; S.I = h->I; S.nh = h->nh;
+    S.n_rows = n; S.row_offset = row_offset; S.ld_logits = ld_logits;
+    S.t_start = d_t_start; S.row_ids = d_row_ids; S.x0_out = d_x0_out; S.logits = d_logits;
+    S.inj_xT = d_inj_xT; S.inj_z = d_inj_z; S.inj_mask = d_inj_mask; S.seed = seed;
+    const int widest = std::max(std::max(h->L, h->D), h->H);
+    const int nt = (widest + 7) / 8;
+    const long long ctas = (n + 16 * SMALL_WARPS - 1) / (16 * SMALL_WARPS);
+    if (ctas > 0x7fffffffLL) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_sample: too many rows for one launch");
+    auto launch = [&](auto kernel, int smem) -> int {
+      SDRM_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      kernel<<<static_cast<unsigned>(ctas), SMALL_THREADS, smem, st>>>(S);
+      SDRM_CUDA(cudaGetLastError());
+      return SDRM_OK;
+    };
+    int rc_s;
+    if (nt <= 3) rc_s = launch(sdrm_small_chain_kernel<3>, SmallGeom<3>::SMEM_BYTES);
+    else if (nt <= 5) rc_s = launch(sdrm_small_chain_kernel<5>, SmallGeom<5>::SMEM_BYTES);
+    else rc_s = launch(sdrm_small_chain_kernel<8>, SmallGeom<8>::SMEM_BYTES);
+    if (rc_s) return rc_s;
+    h->last_launches = 1;
+    h->last_cluster = 0;   // 0 = not the cluster engine
+    return SDRM_OK;
+  }
   int grid, mask_pitch; size_t act, stride, mask_off;
   sample_geometry(h, n, &grid, &act, &stride, &mask_off, &mask_pitch);
   if (workspace_bytes < static_cast<size_t>(grid) * stride) return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small");
@@ -637,6 +742,10 @@ int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
       return SDRM_OK;
     case SDRM_OPT_NO_DISCARD:
       h->no_discard = v != 0;
+      return SDRM_OK;
+    case SDRM_OPT_ENGINE:
+      if (v < 0 || v > 2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: engine must be 0 (auto), 1 (tcgen05 layer engine) or 2 (small-chain kernel)");
+      h->engine_choice = v;
       return SDRM_OK;
     case SDRM_OPT_DEBUG_FLAGS:
 #ifdef SDRM_PERF_DEBUG

@@ -117,7 +117,7 @@ def engine_for(diff_net, device=None):
 
 @torch.no_grad()
 def sample_ddpm(n_sample, diff_net, vae_net, diff_latent_dim, noise_divider=1.0, timesteps=None, n_timesteps=None,
-                verbose=False, *, seed=None, row_offset=0, out=None, return_latent=False, reuse_packed=False):
+                verbose=False, *, seed=None, row_offset=0, out=None, return_latent=False, reuse_packed=False, t_rows=None):
     """Reverse diffusion in the VAE latent space + decode -> float32 logits [n_sample, N_ITEMS] on the GPU.
 
     timesteps='random' is the multi-resolution mode: row j runs only t_j ~ U{1..T-1} steps, t_j drawn from
@@ -125,7 +125,8 @@ def sample_ddpm(n_sample, diff_net, vae_net, diff_latent_dim, noise_divider=1.0,
     in-kernel Philox streams (default: drawn from torch's global generator, so torch.manual_seed makes a run
     reproducible), `row_offset` is the global id of row 0 when the rows are sharded over several GPUs, `reuse_packed=True`
     skips re-packing the weights when the parameter tensors are unchanged since the last call (the default re-packs: ~0.1 ms,
-    and safe against in-place edits through `.data` that no version counter records).
+    and safe against in-place edits through `.data` that no version counter records), `t_rows` gives the multi-resolution
+    chain lengths explicitly (row-sharded callers slice one global draw, sdrm_b200.distributed.sample_ddpm_sharded).
     """
     start_time = time.time()
     diff_net.eval()
@@ -147,11 +148,16 @@ def sample_ddpm(n_sample, diff_net, vae_net, diff_latent_dim, noise_divider=1.0,
     if random_mode:
         if T < 2:
             raise ValueError("multi-resolution sampling needs at least 2 timesteps")
-        t_np = np.random.randint(1, T, size=int(n_sample)).astype(np.int32)
+        t_np = (np.random.randint(1, T, size=int(n_sample)) if t_rows is None else np.asarray(t_rows)).astype(np.int32)
+        if t_np.shape != (int(n_sample),):
+            raise ValueError("t_rows must have n_sample entries")
         order = np.argsort(-t_np, kind="stable").astype(np.int32)  # long chains first: tiles finish together
         t_start = torch.from_numpy(t_np[order])
         row_ids = torch.from_numpy(order)
     latent = torch.empty((n_sample, L), dtype=torch.float32, device=dev) if return_latent else None
+    if int(n_sample) == 0:
+        empty = torch.empty((0, eng.I), dtype=torch.float32, device=dev)
+        return (empty, latent) if return_latent else empty
     samples = eng.sample(int(n_sample), row_offset=int(row_offset), t_start=t_start, row_ids=row_ids, seed=seed,
                          out=out, latent_out=latent)
     if verbose:

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sdrm_denoiser_bwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "sdrm_train_check_device_error": (C.c_int, [_P, _P]),
+    "sdrm_train_launch_count": (C.c_longlong, [C.c_int]),
     "sdrm_gemm_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int64, C.c_int]),
     "sdrm_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, _P, _P, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int,
                             C.c_int, _P, C.c_size_t, _P]),

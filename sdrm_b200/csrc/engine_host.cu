@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -246,7 +247,21 @@ static void free_dec(sdrm_handle* h) {
   h->have_dec = false;
 }
 
+
+// run-time watchdog limit of this translation unit's kernels (ptx_sm100.cuh): SDRM_WATCHDOG_MS in the environment, 0 = none
+static int apply_watchdog_env_k1() {
+  static bool done = false;
+  if (done) return SDRM_OK;
+  done = true;
+  const char* e = getenv("SDRM_WATCHDOG_MS");
+  if (!e || !*e) return SDRM_OK;
+  const unsigned long long ns = strtoull(e, nullptr, 10) * 1000000ull;
+  SDRM_CUDA(cudaMemcpyToSymbol(sdrm::g_sdrm_watchdog_ns, &ns, sizeof ns));
+  return SDRM_OK;
+}
+
 static int engine_set_smem_attr() {
+  { int wrc = apply_watchdog_env_k1(); if (wrc) return wrc; }
   static bool done[64] = {false};
   int dev = 0;
   SDRM_CUDA(cudaGetDevice(&dev));

@@ -460,7 +460,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 for (int j = lane; j < n_lines; j += 32)
                   asm volatile("discard.global.L2 [%0], 128;" ::"l"(dead + static_cast<size_t>(j) * 128) : "memory");
 #endif
+#ifndef SDRM_DISCARD_NOFENCE   // (perf experiment)
                 fence_proxy_async();   // the next writes to these lines are TMA stores (async proxy)
+#endif
               }
               __syncwarp();
               if (lane == 0) mbar_arrive(bar_discard_done(s, k));

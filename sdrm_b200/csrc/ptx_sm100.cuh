@@ -63,10 +63,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
-// Watchdog: a protocol bug must become an error code, never a hung GPU box.
+// Watchdog: a protocol bug must become an error code, never a hung GPU box.  The limit is a run-time value (per translation
+// unit: sdrm_set_watchdog_* in the host files copy it in; environment variable SDRM_WATCHDOG_MS, 0 = no limit), because the
+// global timer keeps running while a context is preempted (time-sliced GPU, debugger, profiler replay) and a healthy run must
+// not be killed there.
 #ifndef SDRM_WATCHDOG_NS
 #define SDRM_WATCHDOG_NS 4000000000ull
 #endif
+static __constant__ unsigned long long g_sdrm_watchdog_ns = SDRM_WATCHDOG_NS;
 // try_wait with a suspend-time hint: the waiting thread is parked by the hardware until the phase completes or the hint
 // (ns) expires, so a waiter neither issues poll instructions nor wakes up late.  (The polling loops with __nanosleep were
 // 45 % of all executed warp instructions of the engine kernel — ncu source page, r01 — and every epilogue warp woke up
@@ -96,7 +100,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     if ((++spins & 0xffu) == 0) {
       const uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > SDRM_WATCHDOG_NS) {
+      else if (g_sdrm_watchdog_ns != 0ull && t - t0 > g_sdrm_watchdog_ns) {
         // (may be mapped host memory: plain accesses.)  Word 0 = the first wait that timed out; word code / 100 (1 producers, 2 UMMA
         // issuer, 3 epilogue, 4 noise, 5 GEMM, 6 discard) = where that role is stuck -- the other roles time out moments later
         if (err_word) {

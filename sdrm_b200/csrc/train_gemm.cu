@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -127,6 +128,8 @@ __global__ void finish_sums_kernel(const double* __restrict__ src, int n, float*
 
 using namespace sdrm;
 
+static thread_local long long g_train_launches = 0;   // kernels of this file launched by the calling thread (bench bookkeeping)
+
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -169,7 +172,21 @@ struct Bf16Mat {   // hi / lo images of one fp32 matrix
   long long rows = 0, cols = 0, ld = 0;
 };
 
+
+// run-time watchdog limit of this translation unit's kernels (ptx_sm100.cuh): SDRM_WATCHDOG_MS in the environment, 0 = none
+static int apply_watchdog_env_k5() {
+  static bool done = false;
+  if (done) return SDRM_OK;
+  done = true;
+  const char* e = getenv("SDRM_WATCHDOG_MS");
+  if (!e || !*e) return SDRM_OK;
+  const unsigned long long ns = strtoull(e, nullptr, 10) * 1000000ull;
+  SDRM_CUDA(cudaMemcpyToSymbol(sdrm::g_sdrm_watchdog_ns, &ns, sizeof ns));
+  return SDRM_OK;
+}
+
 static int gemm_clusters(int* out) {
+  { int wrc = apply_watchdog_env_k5(); if (wrc) return wrc; }
   static int cached[64];
   static bool have[64] = {false};
   int dev = 0;
@@ -262,6 +279,7 @@ static int launch_gemm(const GemmCall& g, int* err_word, cudaStream_t st) {
   attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_gemm_pair_kernel, P));
+  ++g_train_launches;
   return SDRM_OK;
 }
 
@@ -277,6 +295,7 @@ static int launch_prep(const float* src, long long ld_src, long long R, int C, i
   if (grid.y > 65535) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "operand_prep: more than 4 M rows");
   operand_prep_kernel<<<grid, 256, 0, st>>>(P);
   SDRM_CUDA(cudaGetLastError());
+  ++g_train_launches;
   return SDRM_OK;
 }
 
@@ -391,7 +410,7 @@ int sdrm_gemm(const float* d_A, int64_t lda, int trans_a, const float* d_B, int6
   if ((rc = launch_gemm(g, reinterpret_cast<int*>(ws), st))) return rc;
   if (eff > 1) {
     if (d_bias) return sdrm_fail(SDRM_ERR_UNSUPPORTED, "sdrm_gemm: bias with split-K");
-    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, eff, Np, static_cast<int>(M), N, d_C, ldc);
+    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, eff, Np, static_cast<int>(M), N, d_C, ldc); ++g_train_launches;
     SDRM_CUDA(cudaGetLastError());
   }
   return SDRM_OK;
@@ -480,7 +499,7 @@ int sdrm_denoiser_bwd(const float* d_g_out, const float* d_out, const float* d_x
   Bf16Mat GT = mat_at(ws, t.gt, L, rows, t.Rp);
   SDRM_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * t.Wp, st));
   if ((rc = launch_prep(d_g_out, L, rows, L, PREP_TANH_BWD, d_out, L, nullptr, &G, &GT, colsum, st))) return rc;
-  finish_sums_kernel<<<(L + 255) / 256, 256, 0, st>>>(colsum, L, d_gbo);
+  finish_sums_kernel<<<(L + 255) / 256, 256, 0, st>>>(colsum, L, d_gbo); ++g_train_launches;
   // dWo = G^T H_nh^T^T   (A = G^T [L, rows], B = H_nh^T [D, rows])
   Bf16Mat XT = mat_at(ws, t.xt, D, rows, t.Rp);
   if ((rc = launch_prep(pre(nh), t.Dp, rows, D, PREP_PRELU, nullptr, 0, slope_of(nh), nullptr, &XT, nullptr, st))) return rc;
@@ -488,7 +507,7 @@ int sdrm_denoiser_bwd(const float* d_g_out, const float* d_out, const float* d_x
     GemmCall g;
     g.A = GT; g.B = XT; g.passes = passes; g.C = slabs; g.ldc = t.Wp; g.splits = t.splits_o; g.slab_stride = static_cast<long long>(t.slab_elems);
     if ((rc = launch_gemm(g, err, st))) return rc;
-    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, wgrad_splits(L, D, rows, clusters), t.Wp, L, D, d_gWo, D);
+    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, wgrad_splits(L, D, rows, clusters), t.Wp, L, D, d_gWo, D); ++g_train_launches;
   }
   // dH_nh = G Wo, then through PReLU'(pre_nh): the new G
   {
@@ -522,8 +541,8 @@ int sdrm_denoiser_bwd(const float* d_g_out, const float* d_out, const float* d_x
     cur ^= 1;
   }
   if (nh > 0) {
-    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, static_cast<long long>(t.slab_elems), nh * wgrad_splits(D, D, rows, clusters), t.Wp, D, D, d_gWh, D);
-    finish_sums_kernel<<<(D + 255) / 256, 256, 0, st>>>(colsum, D, d_gbh);
+    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, static_cast<long long>(t.slab_elems), nh * wgrad_splits(D, D, rows, clusters), t.Wp, D, D, d_gWh, D); ++g_train_launches;
+    finish_sums_kernel<<<(D + 255) / 256, 256, 0, st>>>(colsum, D, d_gbh); ++g_train_launches;
   }
   // ---- layer 0: dW0[:, :L] = G_0^T x, and the gradient of the time-embedding bias rows
   {
@@ -535,14 +554,20 @@ int sdrm_denoiser_bwd(const float* d_g_out, const float* d_out, const float* d_x
     GemmCall g;
     g.A = GT; g.B = XT; g.passes = passes; g.C = slabs; g.ldc = t.Wp; g.splits = t.splits_0; g.slab_stride = static_cast<long long>(t.slab_elems);
     if ((rc = launch_gemm(g, err, st))) return rc;
-    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, wgrad_splits(D, L, rows, clusters), t.Wp, D, L, d_gW0, L);
+    slab_reduce_kernel<<<296, 256, 0, st>>>(slabs, g.slab_stride, wgrad_splits(D, L, rows, clusters), t.Wp, D, L, d_gW0, L); ++g_train_launches;
     dim3 grid(static_cast<unsigned>(T + 1), static_cast<unsigned>((D + 255) / 256));
-    table_grad_kernel<<<grid, 256, 0, st>>>(Gf, t.Wp, reinterpret_cast<const long long*>(d_order), reinterpret_cast<const long long*>(d_offsets), D, d_gTable, D);
+    table_grad_kernel<<<grid, 256, 0, st>>>(Gf, t.Wp, reinterpret_cast<const long long*>(d_order), reinterpret_cast<const long long*>(d_offsets), D, d_gTable, D); ++g_train_launches;
   }
-  finish_sums_kernel<<<1, 32, 0, st>>>(slope_g, 1, d_ga0);
-  if (nh > 0) finish_sums_kernel<<<1, 32, 0, st>>>(slope_g + 1, 1, d_gah);
+  finish_sums_kernel<<<1, 32, 0, st>>>(slope_g, 1, d_ga0); ++g_train_launches;
+  if (nh > 0) finish_sums_kernel<<<1, 32, 0, st>>>(slope_g + 1, 1, d_gah); ++g_train_launches;
   SDRM_CUDA(cudaGetLastError());
   return SDRM_OK;
+}
+
+long long sdrm_train_launch_count(int reset) {
+  const long long n = g_train_launches;
+  if (reset) g_train_launches = 0;
+  return n;
 }
 
 int sdrm_train_check_device_error(const void* d_workspace, void* stream) {

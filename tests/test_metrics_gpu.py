@@ -66,6 +66,23 @@ def test_topk_float64_scores():
     assert np.array_equal(got, order)
 
 
+@pytest.mark.parametrize("k", [17, 40, 64])
+def test_topk_pooled_kernel_worst_cases(k):
+    """k > 16 runs the pooled kernel (candidate pool + bitonic merge): ascending rows make EVERY element a candidate (a flush
+    per 64 elements), descending rows none after the first flush; float64 scores; against the stable argsort."""
+    from sdrm_b200 import metrics
+    rng = np.random.RandomState(k)
+    base = np.sort(rng.randn(6, 2500).astype(np.float32), axis=1)
+    x = np.concatenate([base, base[:, ::-1], np.repeat(base[:, :1], 2500, axis=1)], axis=0).copy()
+    x[1, 100:164] = x[1, 2400]                     # a run of ties inside an ascending row
+    got = metrics.topk_device(torch.from_numpy(x).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, np.argsort(-x, axis=1, kind="stable")[:, :k])
+    xd = rng.randn(9, 1777)                        # float64, odd width (scalar tail loads)
+    xd[:, 300] = xd[:, 900] + 1e-13
+    got = metrics.topk_device(torch.from_numpy(xd).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, np.argsort(-xd, axis=1, kind="stable")[:, :k])
+
+
 @pytest.mark.parametrize("k", [1, 3, 5, 10, 20, 50])
 def test_recall_ndcg_match_reference_formulas(k):
     """recall_at_k_batch / NDCG_binary_at_k_batch with the reference's numpy formulas (utilities.py:123-171)."""

@@ -280,6 +280,7 @@ def run_ours(args, w, rank, world, local_rank):
     eng.set_option(_l.OPT_CLUSTER, args.cluster)
     eng.set_option(_l.OPT_SUBTILES, args.subtiles)
     eng.set_option(_l.OPT_NO_DISCARD, int(os.environ.get("SDRM_NO_DISCARD", "0")))   # A/B of the dead-buffer discard
+    eng.set_option(_l.OPT_RESIDENT, int(os.environ.get("SDRM_NO_RESIDENT", "0")))   # A/B of the resident (latency) mode
     if int(os.environ.get("SDRM_DEBUG_FLAGS", "0")):    # perf experiments (tools/ablate.sh): -DSDRM_PERF_DEBUG builds only
         eng.set_option(_l.OPT_DEBUG_FLAGS, int(os.environ["SDRM_DEBUG_FLAGS"]))
     for i in range(args.warmup):
@@ -403,7 +404,7 @@ def run_ours(args, w, rank, world, local_rank):
                        **{k: w[k] for k in ("I", "H", "L", "T", "nh", "nd")},
                        "l2": "each step writes n*I*4 bytes of logits (>> 126 MB L2 for cfg5); no reuse across steps",
                        "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
-            "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "subtiles": args.subtiles, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "resident": int(eng.lib.sdrm_last_resident_mode(eng.handle)), "subtiles": args.subtiles, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
         }
         emit(line)

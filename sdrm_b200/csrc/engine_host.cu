@@ -203,6 +203,8 @@ struct sdrm_handle {
   int cluster_override = 0;     // 1 / 2 / 4 / 8
   int subtile_override = 0;     // 1 / 2 row tiles a CTA interleaves
   int no_discard = 0;           // 1 = keep dead activation lines in the L2 (A/B of the discard warp)
+  int no_resident = 0;          // 1 = never keep the chain's activation tile in shared memory (A/B of the resident mode)
+  int last_resident = 0;        // what the last sdrm_sample launch did
   int grid_limit = 0;           // cap on the CTAs of an sdrm_sample launch (tests: small inputs exercise the multi-tile loops)
   int debug_flags = 0;          // -DSDRM_PERF_DEBUG builds only
   unsigned long long* trace = nullptr;   // -DSDRM_TRACE builds only
@@ -703,6 +705,24 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     const int kb_read = std::min(std::min(h->g0.KB, h->nh > 0 ? h->gh.KB : h->g0.KB), h->go.KB);
     P.discard_kb = std::max(0, std::min(written / KBLK, kb_read));
   }
+  // Resident mode (see the kernel): every CTA owns one row tile, and every chain layer fits one pass of the accumulators
+  // (N <= 2 chunks = 512 TMEM columns) and the part of the stage ring the weight stream can spare (<= 8 k-blocks).
+  P.resident = 0; P.res_nstg = 0;
+  if (cluster == 2 && n_local == 1 && P.n_sub == 1 && P.n_step > 0 && !h->no_resident) {
+    int kb_max = 0;
+    bool ok = true;
+    for (int j = 0; j < P.n_step; ++j) {
+      const LayerDesc& d = P.step[j];
+      ok = ok && d.NCH <= 2 && d.passes == 1;
+      kb_max = std::max(kb_max, std::max(d.KB, (d.NCH * d.NC + KBLK - 1) / KBLK));
+    }
+    if (ok && kb_max <= 8) {
+      P.resident = 1;
+      P.res_nstg = kb_max <= 6 ? 3 : 2;
+      P.discard_kb = 0;
+    }
+  }
+  h->last_resident = P.resident;
   if (static_cast<size_t>(launch_grid) * P.n_sub * stride > workspace_bytes)
     return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small for the sub-tile scratch slots");
   rc = launch_engine(P, launch_grid, cluster, st);
@@ -712,6 +732,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
 }
 
 int sdrm_last_launch_count(const sdrm_handle* h) { return h ? h->last_launches : 0; }
+int sdrm_last_resident_mode(const sdrm_handle* h) { return h ? h->last_resident : 0; }
 
 int sdrm_check_device_error(sdrm_handle* h, void* stream) {
   if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "null handle");
@@ -757,6 +778,10 @@ int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
       return SDRM_OK;
     case SDRM_OPT_NO_DISCARD:
       h->no_discard = v != 0;
+      return SDRM_OK;
+    case SDRM_OPT_RESIDENT:
+      if (v < 0 || v > 1) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: resident must be 0 (automatic) or 1 (off)");
+      h->no_resident = v;
       return SDRM_OK;
     case SDRM_OPT_ENGINE:
       if (v < 0 || v > 2) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: engine must be 0 (auto), 1 (tcgen05 layer engine) or 2 (small-chain kernel)");

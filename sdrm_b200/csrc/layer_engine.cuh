@@ -53,7 +53,8 @@ enum EpiKind : int { EPI_PRELU = 0, EPI_POSTERIOR = 1, EPI_TANH_SPLIT = 2, EPI_L
 
 // error codes the device watchdog writes (which wait timed out)
 enum : int { WD_PRODUCER_EMPTY = 101, WD_PRODUCER_ACT = 102, WD_PRODUCER_TILE = 103, WD_MMA_FULL = 201,
-             WD_MMA_ACC = 202, WD_MMA_TILE = 203, WD_EPI_ACC = 301, WD_EPI_NOISE = 302, WD_EPI_DISCARD = 303, WD_NOISE_STATE = 401, WD_NOISE_TILE = 402, WD_DISCARD = 601 };
+             WD_MMA_ACC = 202, WD_MMA_TILE = 203, WD_EPI_ACC = 301, WD_EPI_NOISE = 302, WD_EPI_DISCARD = 303, WD_NOISE_STATE = 401, WD_NOISE_TILE = 402, WD_DISCARD = 601,
+             WD_MMA_AREADY = 204, WD_MMA_PEER = 205, WD_RELAY = 701, WD_EPI_LAYER = 304 };
 
 struct LayerDesc {
   const uint8_t* w_img;   // weight images [which: hi, lo][chunk][k block][NC rows x 128 B], 128B-swizzled
@@ -94,6 +95,8 @@ struct ChainParams {
   size_t mask_off;        // per-CTA scratch: offset of the dropout keep bits [128 rows][mask_pitch bytes] (bit c of a row = column c)
   int mask_pitch;         // bytes per row of keep bits: 16 * ceil(Lg16 / 8)
   int discard_kb;         // pair mode: k-blocks of a chain layer's dead input image the discard warp drops from the L2 (0 = off)
+  int resident;           // pair mode, one row tile per CTA: the chain's activation tile lives in shared memory (see the kernel)
+  int res_nstg;           // resident mode: pipeline stages left to the weight / decoder stream (the rest of the ring holds the tile)
   int* err_word;
   // pair mode only: TMA tensor maps over the weight blobs (rows of 128 B, box = NC/2 rows) and over the whole
   // activation scratch (box = 128 rows); tensor-map loads may complete on the LEADER CTA's mbarrier (.cta_group::2)

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
-  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6);   // mbarriers of a CTA (map below)
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 2;   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
   constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -155,6 +155,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // phases of a sub-tile are outstanding and a single barrier would be lapped (parity aliasing = deadlock).
   auto bar_layer_consumed = [&](uint32_t s, uint32_t k) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + 2 * MAX_SUB + 2 * s + (k & 1u)); };
   auto bar_discard_done = [&](uint32_t s, uint32_t k) { return bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * MAX_ACT_CHUNKS + 4 * MAX_SUB + 2 * s + (k & 1u)); };
+  // resident mode: a_ready = this CTA's epilogue warps have written the whole input tile of the next chain layer into shared
+  // memory; peer_ready (leader's copy) = the same for the peer CTA, relayed by the peer's otherwise idle UMMA warp
+  const uint32_t bar_a_ready = bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6));
+  const uint32_t bar_peer_ready = bar_a_ready + 8u;
   // per-role layer counters: two bits per sub-tile (k mod 4 is all the ring index and the parity need)
   auto cnt_get = [](uint32_t cnt, int s) -> uint32_t { return (cnt >> (2 * s)) & 3u; };
   auto cnt_inc = [](uint32_t cnt, int s) -> uint32_t { return (cnt & ~(3u << (2 * s))) | ((((cnt >> (2 * s)) + 1u) & 3u) << (2 * s)); };
@@ -190,6 +194,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       }
     }
     mbar_init(bar_tile_ready, EPI_WARPS);
+    mbar_init(bar_a_ready, EPI_WARPS);
+    mbar_init(bar_peer_ready, 1);
     fence_mbar_init();
   }
   if (warp == M_WARP) {
@@ -201,6 +207,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   if (PAIR) cluster_sync_all();   // the peer's barriers exist before anyone commits / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Resident mode (pair mode, every CTA owns ONE row tile: the dataset-sized configurations, where a layer's latency and not
+  // the tensor throughput is what counts).  The chain's activation tile [128 rows x K] never leaves the SM: it lives in the
+  // part of the stage ring the weight stream does not use (res_nstg stages stay), as KB k-block images in the UMMA operand
+  // layout.  A chain layer accumulates ALL its N <= 512 columns in TMEM (chunk c in accumulator c), and once the layer's last
+  // UMMA has retired the epilogue warps overwrite the tile in place with the layer's output (bias / PReLU / posterior update /
+  // dropout / bf16) -- no TMA store, no L2 round trip, no chunk barriers: the hand-off is one proxy fence and one mbarrier
+  // (the peer CTA's half of the M = 256 operand is signalled through its idle UMMA warp with a cluster-scope release).  The
+  // weights still stream from the L2; x_0 goes to the scratch as bf16 hi / lo and the decoder runs as in streaming mode.
+  const bool RES = PAIR && P.resident != 0;
+  const uint32_t nstg = RES ? static_cast<uint32_t>(P.res_nstg) : static_cast<uint32_t>(NSTG);
+  const uint32_t res_a = base_addr + nstg * STG_BYTES;
 
   const long long n_tiles = (P.n_rows + TILE_M - 1) / TILE_M;
   const long long n_clusters = gridDim.x / NCTA;
@@ -261,8 +278,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       // kb only needs the chunks covering features < 64 (kb + 1), so a layer starts while the previous layer's last
       // chunk is still in its epilogue.
       int prev_nch = 0, prev_nc = 1;
-      auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf, int s) {
+      auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf, int s, bool res_layer) {
         const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes;
+        if (res_layer && !is_w) {
+          // the activation producer sits a resident chain layer out: it only keeps its ring position in step (it meets the ring
+          // again at the decoder's first k-block, after the x_0 pass -- by then every chain UMMA has retired, so its parity
+          // cannot alias an older phase)
+          const uint32_t pos = stage + static_cast<uint32_t>(NCH * passes * ((KB + 1) >> 1));   // (two weight k-blocks per stage)
+          sphase ^= (pos / nstg) & 1u;
+          stage = pos % nstg;
+          return;
+        }
         const uint8_t* w_img = ldref.w_img;
         const uint8_t* sc = scratch_of(tile_of(it, s), s);
         const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
@@ -281,7 +307,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank & 1u) * half_rows +
                         (CS > 2 ? static_cast<int>(pair_idx) * part_rows : 0);
             int a_row = a_row_base + static_cast<int>((static_cast<size_t>(a_buf) * P.act_buf_bytes) >> 7);
-            for (int kb = 0; kb < KB; ++kb) {
+            // resident chain layers: a stage has no activation half to fill, so it carries TWO weight k-blocks (the second in the
+            // activation half): twice the weight bytes in flight -- this mode is bound by the L2 latency of the weight stream
+            const int kstep = res_layer ? 2 : 1;
+            for (int kb = 0; kb < KB; kb += kstep) {
               if (!is_w && c == 0 && p == 0) {
                 int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
                 if (need > prev_nch || kb == KB - 1) need = prev_nch;
@@ -300,8 +329,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   // producers arm it with the bytes of both CTAs
                   const uint32_t fb0 = mapa_cluster(fb, leader_rank);
                   if (is_w) {
-                    if (cta_rank == leader_rank) mbar_arrive_expect_tx(fb, w_bytes);
-                    if (CS > 2) {
+                    const bool two = res_layer && kb + 1 < KB;
+                    if (cta_rank == leader_rank) {
+                      mbar_arrive_expect_tx(fb, two ? 2u * w_bytes : w_bytes);
+                      if (res_layer) mbar_arrive(fb);   // resident chain layer: no activation load takes the stage's second arrival
+                    }
+                    if (res_layer) {
+                      tma_load_2d_pair_hint(mapa_cluster(stage_a(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
+                      if (two) tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row + NC, fb0, pol_keep);
+                    } else if (CS > 2) {
                       // this CTA's 1/CS of the k-block goes to the same smem offset of every CTA holding this N-half;
                       // each copy completes on the full barrier of the destination's own pair leader
                       constexpr uint16_t kHalfMask = static_cast<uint16_t>(CS == 8 ? 0x55u : 0x05u);
@@ -323,12 +359,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 }
               }
               __syncwarp();
-              w_row += NC;
+              w_row += NC * kstep;
               a_row += A_TILE_BYTES >> 7;
               w_src += w_bytes;
               a_src += A_TILE_BYTES;
               if (!is_w) { SDRM_TR(0, 5); SDRM_TR_SEQ(); }
-              if (++stage == NSTG) { stage = 0; sphase ^= 1; }
+              if (++stage == nstg) { stage = 0; sphase ^= 1; }
             }
           }
           if (!is_w) SDRM_TR(0, 3);
@@ -344,12 +380,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       int cur = 0;
       for (int i = T_tile; i >= 1; --i)
         for (int l = 0; l < P.n_step; ++l) {
-          for (int s = 0; s < ns; ++s) run(P.step[l], &P.tm_step_w[l], cur, cur, s);
+          for (int s = 0; s < ns; ++s) run(P.step[l], &P.tm_step_w[l], cur, cur, s, RES);
           done(P.step[l]);
           cur ^= 1;
         }
       for (int l = 0; l < P.n_dec; ++l) {
-        for (int s = 0; s < ns; ++s) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo, s);
+        for (int s = 0; s < ns; ++s) run(P.dec[l], &P.tm_dec_w[l], P.dec[l].in_hi == 0 ? cur : cur ^ 1, P.dec[l].in_lo, s, false);
         done(P.dec[l]);
       }
     }
@@ -357,10 +393,22 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     setmaxnreg_dec<REGS_CTRL>();
     if (PAIR && cta_rank != leader_rank) {
       // peer CTA of a pair: the leader issues every UMMA; the peer's TMA loads complete on the leader's barriers
+      if (RES) {
+        // resident mode: relay "this CTA's half of the next layer's input tile is written" to the leader.  The epilogue warps
+        // arrive on the local barrier (CTA-scope release behind their proxy fence); this thread has no memory operation of its
+        // own in flight, so its cluster-scope release costs nothing (an epilogue thread's would wait for its state stores).
+        const uint32_t remote = mapa_cluster(bar_peer_ready, leader_rank);
+        const int n_layers = P.T * P.n_step;
+        for (int k = 0; k < n_layers; ++k) {
+          mbar_wait(bar_a_ready, static_cast<uint32_t>(k) & 1u, err, WD_RELAY);
+          if (elect_one()) mbar_arrive_cluster_release(remote);
+          __syncwarp();
+        }
+      }
     } else {
       // ======================================= UMMA issuer ========================================
       // whole warp converged, one elected lane issues (see the producer comment)
-      uint32_t stage = 0, sphase = 0, cc = 0, lc_cnt = 0;
+      uint32_t stage = 0, sphase = 0, cc = 0, lc_cnt = 0, a_par = 0;
       for (int it = 0; it < n_iters; ++it) {
         if (!PAIR && tile_of(it, 0) >= n_tiles) break;
         const int ns = nsub_of(it);
@@ -372,6 +420,16 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         auto run = [&](const LayerDesc& ldref, int s, bool chain) {
           const int KB = ldref.KB, NCH = ldref.NCH, passes = ldref.passes, kmma_last = ldref.kmma_last;
           const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ldref.NC);
+          const bool res_layer = RES && chain;
+          if (res_layer) {
+            // both halves of the M = 256 input tile are in place (and the previous layer's accumulators have been read)
+            mbar_wait(bar_a_ready, a_par, err, WD_MMA_AREADY);
+            mbar_wait(bar_peer_ready, a_par, err, WD_MMA_PEER);
+            a_par ^= 1u;
+            fence_acq_rel_cluster();
+            tc_fence_after();
+            SDRM_TR(1, 7);
+          }
           for (int c = 0; c < NCH; ++c) {
             const uint32_t buf = cc & 1u;
             SDRM_TR(1, 1);
@@ -381,16 +439,30 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             const uint32_t d_tmem = tmem_base + buf * 256u;
             uint32_t acc = 0;
             for (int p = 0; p < passes; ++p) {
-              for (int kb = 0; kb < KB; ++kb) {
+              for (int kb = 0; kb < KB; kb += (res_layer ? 2 : 1)) {
                 mbar_wait(bar_full(stage), sphase, err, WD_MMA_FULL);
                 tc_fence_after();
                 SDRM_TR(1, kb == 0 && p == 0 ? 3 : 5);
-                const uint64_t a_desc = umma_desc_sw128(stage_a(stage));
-                const uint64_t b_desc = umma_desc_sw128(stage_w(stage));
+                const uint64_t a_desc = umma_desc_sw128(res_layer ? res_a + static_cast<uint32_t>(kb) * A_TILE_BYTES : stage_a(stage));
+                const uint64_t b_desc = umma_desc_sw128(res_layer ? stage_a(stage) : stage_w(stage));
                 const int nk = (kb == KB - 1) ? kmma_last : 4;
                 if (elect_one()) {
                   // +32 B (16 bf16) along K inside the swizzle row = +2 in the 16-byte address field
-                  if (PAIR) {
+                  if (PAIR && res_layer && kb + 1 < KB) {
+                    // resident chain layer: the stage holds two weight k-blocks (see the producer)
+                    const uint64_t a2 = umma_desc_sw128(res_a + static_cast<uint32_t>(kb + 1) * A_TILE_BYTES);
+                    const uint64_t b2 = umma_desc_sw128(stage_w(stage));
+                    const int nk2 = (kb + 1 == KB - 1) ? kmma_last : 4;
+                    umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, acc);
+                    umma_bf16_ss_pair(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
+                    umma_bf16_ss_pair(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
+                    umma_bf16_ss_pair(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
+                    umma_bf16_ss_pair(d_tmem, a2, b2, idesc, 1u);
+                    if (nk2 > 1) umma_bf16_ss_pair(d_tmem, a2 + 2u, b2 + 2u, idesc, 1u);
+                    if (nk2 > 2) umma_bf16_ss_pair(d_tmem, a2 + 4u, b2 + 4u, idesc, 1u);
+                    if (nk2 > 3) umma_bf16_ss_pair(d_tmem, a2 + 6u, b2 + 6u, idesc, 1u);
+                    umma_commit_pair(bar_empty(stage), static_cast<uint16_t>((1u << CS) - 1u));
+                  } else if (PAIR) {
                     umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, acc);
                     if (nk > 1) umma_bf16_ss_pair(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
                     if (nk > 2) umma_bf16_ss_pair(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
@@ -408,7 +480,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 acc = 1;
                 SDRM_TR(1, 6);
                 SDRM_TR_SEQ();
-                if (++stage == NSTG) { stage = 0; sphase ^= 1; }
+                if (++stage == nstg) { stage = 0; sphase ^= 1; }
               }
             }
             if (elect_one()) {
@@ -536,6 +608,22 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       pend_x = (f0 & 63) * 2;
       if (OUT_SLOTS_PER_WARP == 1) flush_pending();
     };
+    // resident mode: the same 16 features go straight into the shared-memory operand tile (k-block f0 / 64, row r, the two
+    // 16-byte chunks of the 128-byte row XOR-swizzled with r % 8 exactly as a SWIZZLE_128B tensor load would place them)
+    const uint32_t res_row = res_a + static_cast<uint32_t>(r) * 128u;
+    const uint32_t res_xor = static_cast<uint32_t>(r & 7);
+    auto store_res = [&](int f0, const uint32_t (&pk)[8]) {
+      const uint32_t blk = res_row + static_cast<uint32_t>(f0 >> 6) * A_TILE_BYTES;
+      const uint32_t j = static_cast<uint32_t>(f0 & 63) >> 3;
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + ((j ^ res_xor) << 4)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (((j + 1u) ^ res_xor) << 4)), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+    };
+    // this warp's part of the resident tile is written: visible to the tensor core (async proxy), then one arrival per warp
+    auto res_publish = [&]() {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane0) mbar_arrive(bar_a_ready);
+    };
     // all TMA stores of this warp have been written (lane 0 issued them): what a chunk / tile publication waits for
     auto stores_done = [&]() {
       flush_pending();
@@ -563,6 +651,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
         for (size_t i = threadIdx.x; i < n16; i += EPI_THREADS) z[i] = make_uint4(0, 0, 0, 0);
       }
+      epi_bar_sync();
+    }
+    if (RES) {   // K-padding columns of the resident tile must read as exact zeros too
+      const uint32_t n16 = (static_cast<uint32_t>(NSTG) - nstg) * STG_BYTES / 16u;
+      for (uint32_t i = threadIdx.x; i < n16; i += EPI_THREADS)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(res_a + i * 16u), "r"(0u) : "memory");
       epi_bar_sync();
     }
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
@@ -651,7 +745,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             }
             uint32_t pk[8];
             dropout_pack(x, keep, pk);
-            store_act(in0_row, g * 16, pk);
+            if (RES) store_res(g * 16, pk);
+            else store_act(in0_row, g * 16, pk);
           }
         }
       }
@@ -659,6 +754,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       fence_proxy_async();   // the zero fill of the buffers (generic stores) is read by the TMA loads too
       stores_done();
       if (lane == 0) mbar_arrive(bar_tile_ready);
+      if (RES && P.n_step > 0) res_publish();   // the first chain layer's input tile
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
       auto run = [&](auto kind_c, const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) {
@@ -687,7 +783,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         }
         const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
-        const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step;
+        const bool res_layer = RES && (KIND == EPI_PRELU || KIND == EPI_POSTERIOR);   // (chain layers; the decoder streams)
+        const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step && !res_layer;
+        if (res_layer) {
+          // the layer's output overwrites its own input tile: every UMMA of the layer (all chunks) must have retired first.
+          // (A parity wait does not consume the phase: the chunk loop below waits for the same phases again and falls through.)
+          const uint32_t cl = cc + static_cast<uint32_t>(NCH) - 1u;
+          mbar_wait(bar_acc_full(cl & 1u), (cl >> 1) & 1u, err, WD_EPI_LAYER);
+        }
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
         // warp stages the 16 floats of each of its own groups of a chunk in a private shared-memory slice (lane l < 4 BIAS_SLOTS
         // holds elements 4l .. 4l+3: group slot l / 4, columns 4 (l % 4) ..) one chunk ahead, and the group loop reads them with LDS.128.
@@ -780,7 +883,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   pk[e] = pack_bf16x2(a0, a1);
                 }
               }
-              if (!SDRM_DEBUG_SKIP_ACT_STORES) store_act(out_hi_row, f0, pk);
+              if (res_layer) store_res(f0, pk);
+              else if (!SDRM_DEBUG_SKIP_ACT_STORES) store_act(out_hi_row, f0, pk);
             } else if (KIND == EPI_POSTERIOR) {
               // x_{i-1} = (x_i - eps (1-a_i)/sqrt(1-ab_i)) / sqrt(a_i) + sqrt(b_i) nd z; the state already holds
               // x_i / sqrt(a_i) + sqrt(b_i) nd z (noise warps), so only the eps term is left.  Padding columns need no
@@ -800,7 +904,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                 {
                   uint32_t pk[8];
                   dropout_pack(xn, keep, pk);
-                  store_act(out_hi_row, f0, pk);
+                  if (res_layer) { if (!last_step) store_res(f0, pk); }
+                  else store_act(out_hi_row, f0, pk);
                 }
                 if (g + EPI_SUB < ngroups) request_state(g + EPI_SUB);   // xn is dead: fetch the next group's state columns
               }
@@ -877,6 +982,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               for (int c = 0; c < NCH; ++c) mbar_arrive(bar_act_chunk(s, c));
           }
         }
+        if (res_layer && !last_step) { res_publish(); SDRM_TR_EPI(5); }   // the next chain layer's input tile is complete (this warp's part)
         if (KIND == EPI_POSTERIOR && !last_step) {
           __syncwarp();
           if (lane0) mbar_arrive(bar_state_ready(s));   // x_{i-1} is complete: the noise warps may prepare step i-1

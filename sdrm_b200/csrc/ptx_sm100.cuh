@@ -301,6 +301,12 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   // first drain every outstanding global store of the thread (measured: ~10 us per epilogue chunk)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// arrive with a CLUSTER-scope release: what the issuing thread observed / wrote before is visible to the CTA that owns the barrier
+// (only for threads without outstanding global stores: see above)
+__device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

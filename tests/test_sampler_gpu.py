@@ -111,6 +111,35 @@ def test_single_and_pair_mode_are_bit_identical():
         assert torch.equal(outs[1], outs[c]), c
 
 
+@pytest.mark.parametrize("shape", [
+    # n, I, H, L, T, nh       resident geometry
+    (1500, 700, 200, 264, 7, 2),     # KB = 5 (odd: a lone last weight k-block), 2 chunks, 3 stages left
+    (900, 300, 128, 120, 9, 1),      # one chunk, KB = 2
+    (2000, 729, 550, 400, 6, 0),     # cfg-4 widths: KB = 7 -> 2 stages left, no hidden layer
+    (1000, 500, 300, 512, 5, 1),     # the widest denoiser the mode takes (2 x 256 columns, KB = 8)
+    (700, 400, 200, 520, 4, 1),      # too wide (3 chunks): stays in streaming mode
+])
+def test_resident_mode_is_bit_identical_to_streaming(shape):
+    """Pair-mode launches in which every CTA owns one row tile keep the chain's activation tile in shared memory (resident
+    mode); SDRM_OPT_RESIDENT = 1 forces the L2-streaming path.  Same arithmetic, same rows."""
+    from sdrm_b200 import _lib
+    lib = _lib.load()
+    n, I, H, L, T, nh = shape
+    diff, vae = random_modules(I, H, L, T, nh, seed=11, device="cuda")
+    eng = _engine(diff, vae, T, 1.0)
+    lat_a = torch.empty(n, L, device="cuda")
+    lat_b = torch.empty(n, L, device="cuda")
+    a = eng.sample(n, seed=5, latent_out=lat_a, check=True).clone()
+    assert lib.sdrm_last_resident_mode(eng.handle) == (1 if L <= 512 else 0)
+    try:
+        eng.set_option(_lib.OPT_RESIDENT, 1)
+        b = eng.sample(n, seed=5, latent_out=lat_b, check=True)
+        assert lib.sdrm_last_resident_mode(eng.handle) == 0
+    finally:
+        eng.set_option(_lib.OPT_RESIDENT, 0)
+    assert torch.equal(a, b) and torch.equal(lat_a, lat_b)
+
+
 def test_interleaved_sub_tiles_are_bit_identical():
     """A CTA pair that owns several row tiles interleaves two of them layer by layer (ChainParams::n_sub = 2, an odd last
     tile runs alone); the grid cap makes a small launch take that path (12 row tiles on 2 pairs = 3 tiles per CTA)."""

@@ -782,15 +782,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           noise_par ^= 1u << s;
         }
         const bool vec_out = ((P.ld_logits & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.logits) & 15) == 0);
+        const bool lin_rows = P.row_ids == nullptr;   // the warp's 32 rows are consecutive rows of the logits matrix (row = physical row)
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
         const bool res_layer = RES && (KIND == EPI_PRELU || KIND == EPI_POSTERIOR);   // (chain layers; the decoder streams)
         const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step && !res_layer;
-        if (res_layer) {
-          // the layer's output overwrites its own input tile: every UMMA of the layer (all chunks) must have retired first.
-          // (A parity wait does not consume the phase: the chunk loop below waits for the same phases again and falls through.)
-          const uint32_t cl = cc + static_cast<uint32_t>(NCH) - 1u;
-          mbar_wait(bar_acc_full(cl & 1u), (cl >> 1) & 1u, err, WD_EPI_LAYER);
-        }
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
         // warp stages the 16 floats of each of its own groups of a chunk in a private shared-memory slice (lane l < 4 BIAS_SLOTS
         // holds elements 4l .. 4l+3: group slot l / 4, columns 4 (l % 4) ..) one chunk ahead, and the group loop reads them with LDS.128.
@@ -800,6 +795,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           return (lane < 4 * BIAS_SLOTS && slice_g < ngroups) ? *reinterpret_cast<const float4*>(bias_row + c * NC + slice_o) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         float4 bnext = fetch_slice(0);
+        if (res_layer) {
+          // the layer's output overwrites its own input tile: every UMMA of the layer (all chunks) must have retired first.
+          // (A parity wait does not consume the phase: the chunk loop below waits for the same phases again and falls through.)
+          const uint32_t cl = cc + static_cast<uint32_t>(NCH) - 1u;
+          mbar_wait(bar_acc_full(cl & 1u), (cl >> 1) & 1u, err, WD_EPI_LAYER);
+        }
         for (int c = 0; c < NCH; ++c) {
           const uint32_t buf = cc & 1u;
           const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
@@ -922,16 +923,39 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               store_act(out_hi_row, f0, ph);
               store_act(out_lo_row, f0, pl);
             } else {  // EPI_LINEAR_OUT
-              if (valid) {
-                if (vec_out && (f0 + 16 <= n_valid)) {
+              if (vec_out && (f0 + 16 <= n_valid)) {
+                if (valid) {
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
                     __stcs(reinterpret_cast<float4*>(orow + f0) + j, make_float4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]));
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 16; ++e)
-                    if (f0 + e < n_valid) orow[f0 + e] = h[e];
                 }
+              } else if (lin_rows) {
+                // Rows that are not 16-byte aligned (an item count that is no multiple of 4: ml-1m 3 125, ALB 729): 16 scalar stores
+                // per thread are 16 warp instructions of 32 four-byte pieces in 32 different rows -- 512 partial-sector writes per
+                // group, and the decoder epilogue, not its UMMAs, set the pace (timeline: 25 us per 256-column chunk against 6.5 us
+                // of tensor work).  Instead the group goes through the warp's shared-memory slot 8 columns at a time and is written
+                // with lanes along the columns: one instruction = 4 rows x 32 contiguous bytes.
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  if (elect_one()) bulk_wait_group_read<0>();   // (a TMA store of the previous layer may still be reading the slot)
+                  __syncwarp();
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane), "f"(h[8 * hf]), "f"(h[8 * hf + 1]), "f"(h[8 * hf + 2]), "f"(h[8 * hf + 3]) : "memory");
+                  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(out_lane + 16u), "f"(h[8 * hf + 4]), "f"(h[8 * hf + 5]), "f"(h[8 * hf + 6]), "f"(h[8 * hf + 7]) : "memory");
+                  __syncwarp();
+                  const int col = f0 + 8 * hf + (lane & 7);
+#pragma unroll
+                  for (int i4 = 0; i4 < 8; ++i4) {
+                    const int rr = 4 * i4 + (lane >> 3);
+                    float val;
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(val) : "r"(out_slot + static_cast<uint32_t>(rr * 32 + (lane & 7) * 4)) : "memory");
+                    if (row - lane + rr < P.n_rows && col < n_valid) __stcs(orow + static_cast<long long>(rr - lane) * P.ld_logits + col, val);
+                  }
+                  __syncwarp();
+                }
+              } else if (valid) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (f0 + e < n_valid) orow[f0 + e] = h[e];
               }
             }
           }

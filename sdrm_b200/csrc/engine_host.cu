@@ -270,8 +270,7 @@ static int engine_set_smem_attr() {
   if (dev < 64 && done[dev]) return SDRM_OK;
   SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
-  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
-  SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute((sdrm_layer_engine_kernel<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return SDRM_OK;
 }
@@ -288,9 +287,8 @@ static int max_resident_ctas(int cluster, int num_sms) {
   attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   int n = 0;
-  cudaError_t e = cluster == 2   ? cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<2>, &cfg)
-                  : cluster == 4 ? cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<4>, &cfg)
-                                 : cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<8>, &cfg);
+  if (cluster != 2) return 0;
+  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<2>, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n * cluster;
 }
@@ -369,9 +367,8 @@ static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream
   attr.id = cudaLaunchAttributeClusterDimension;
   attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
-  if (cluster == 2) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<2>, P));
-  else if (cluster == 4) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<4>, P));
-  else if (cluster == 8) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<8>, P));
+  if (cluster == 2 && P.resident) SDRM_CUDA(cudaLaunchKernelEx(&cfg, (sdrm_layer_engine_kernel<2, true>), P));
+  else if (cluster == 2) SDRM_CUDA(cudaLaunchKernelEx(&cfg, sdrm_layer_engine_kernel<2>, P));
   else return sdrm_fail(SDRM_ERR_BAD_ARG, "launch_engine: cluster size");
   return SDRM_OK;
 }
@@ -415,8 +412,6 @@ int sdrm_create(sdrm_handle** out, int device) {
   if (engine_set_smem_attr() != SDRM_OK) { delete h; return SDRM_ERR_CUDA; }
   h->resident[1] = h->num_sms;
   h->resident[2] = max_resident_ctas(2, h->num_sms);
-  h->resident[4] = max_resident_ctas(4, h->num_sms);
-  h->resident[8] = max_resident_ctas(8, h->num_sms);
   *out = h;
   return SDRM_OK;
 }
@@ -562,8 +557,7 @@ static void sample_geometry(const sdrm_handle* h, int64_t n, int* grid, size_t* 
   *stride = NUM_ACT_BUFS * (*act_bytes) + xs + static_cast<size_t>(TILE_M) * pitch;
   // a CTA that owns two or more row tiles interleaves them in pairs: one scratch slot per sub-tile
   int min_res = h->num_sms;
-  for (int c = 2; c <= 8; c <<= 1)
-    if (h->resident[c] > 0) min_res = std::min(min_res, h->resident[c]);
+  if (h->resident[2] > 0) min_res = std::min(min_res, h->resident[2]);
   if (n_tiles > min_res) *grid *= MAX_SUB;
 }
 
@@ -665,7 +659,6 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.err_word = h->err_word;
   P.trace = h->trace;
   P.debug_flags = h->debug_flags;
-  // cluster choice: share the weight stream between 4 (or 2) row tiles when the chain is the same for all of them
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
   // full-resolution chains run on tcgen05 cta_group::2 CTA pairs (fewer weight bytes and more k-blocks in flight per SM);
@@ -705,10 +698,13 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     const int kb_read = std::min(std::min(h->g0.KB, h->nh > 0 ? h->gh.KB : h->g0.KB), h->go.KB);
     P.discard_kb = std::max(0, std::min(written / KBLK, kb_read));
   }
-  // Resident mode (see the kernel): every CTA owns one row tile, and every chain layer fits one pass of the accumulators
-  // (N <= 2 chunks = 512 TMEM columns) and the part of the stage ring the weight stream can spare (<= 8 k-blocks).
+  // Resident mode (see the kernel): every chain layer fits one pass of the accumulators (N <= 2 chunks = 512 TMEM columns) and
+  // the part of the stage ring the weight stream can spare (<= 8 k-blocks).  Built for the latency regime (one row tile per CTA:
+  // cfg 4 1.40 -> 1.31 ms), it also wins when a CTA owns several tiles: at these widths the streaming path is bound by L2 bandwidth
+  // (~9 TB/s of activation re-reads, weights, stores and state at 148 CTAs), and the resident tile removes the activation half of it
+  // (cfg-2 widths, 100 000 users: 14.91 -> 14.39 ms; cfg-4 widths, 60 000 users: 5.55 -> 5.26 ms).
   P.resident = 0; P.res_nstg = 0;
-  if (cluster == 2 && n_local == 1 && P.n_sub == 1 && P.n_step > 0 && !h->no_resident) {
+  if (cluster == 2 && P.n_sub == 1 && P.n_step > 0 && h->no_resident != 1) {
     int kb_max = 0;
     bool ok = true;
     for (int j = 0; j < P.n_step; ++j) {
@@ -766,7 +762,7 @@ int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
   const int v = static_cast<int>(value);
   switch (option) {
     case SDRM_OPT_CLUSTER:
-      if (!(v == 0 || v == 1 || v == 2 || v == 4 || v == 8)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: cluster must be 0, 1, 2, 4 or 8");
+      if (!(v == 0 || v == 1 || v == 2)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: cluster must be 0 (automatic), 1 or 2");
       h->cluster_override = v;
       return SDRM_OK;
     case SDRM_OPT_SUBTILES:

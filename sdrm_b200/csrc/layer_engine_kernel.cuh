@@ -106,14 +106,17 @@ __device__ __forceinline__ void xs_store16(float* xs, int g16, int r, const floa
 //               32 KB and 7 of them fit -> 75 % more k-blocks in flight per SM, and half the weight bytes per SM.
 //               The L2 round trip under load (~1.5 us) times the bytes per k-block is what bounds this kernel
 //               (Little's law on 192 KB of staging), which is why the pair mode is the fast path.
-//               CS = 4 / 8: a cluster of CS/2 such pairs that run the same layer sequence in lock step and SHARE the weight
-//               stream: every CTA loads 1/CS of a weight k-block and TMA-multicasts it to the CTAs of the other pairs
-//               that hold the same N-half, so the L2 -> SM weight traffic per SM drops by CS/2.  The kernel is bound by
-//               L2 bandwidth (A re-reads + weights), not by the tensor pipe, which is why this pays.
-template <int CS>
+//               (r01 / r02 also carried CS = 4 / 8: clusters of 2 / 4 pairs in lock step that shared one TMA-multicast weight
+//               stream.  They never won: only 132 of the 148 SMs can hold clusters of 4, and a CS = 4 launch on those plus a
+//               CS = 2 launch on the other 16 SMs measured 4.04 row tiles per ms against 4.02 for CS = 2 everywhere
+//               (profiles/k1_bound_r02.txt): the kernel is bound by board power, not by L2 -> SM bytes.  Pruned.)
+// RESK: the resident-mode instantiation (see below).  A template parameter, not a run-time flag: the streaming instantiation must not
+// carry the mode's branches in the single-thread UMMA issue loop and in the epilogue group loops (measured: +1.2 % per cfg-5 shard).
+template <int CS, bool RESK = false>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
-  constexpr bool PAIR = CS >= 2;
-  constexpr int NPAIRS = PAIR ? CS / 2 : 1;
+  static_assert(!RESK || CS == 2, "resident mode runs on CTA pairs");
+  static_assert(CS == 1 || CS == 2, "single CTAs or one tcgen05 pair per cluster");
+  constexpr bool PAIR = CS == 2;
   constexpr int NSTG = PAIR ? SDRM_NSTG_PAIR : 4;
   constexpr uint32_t W_STAGE_BYTES = PAIR ? static_cast<uint32_t>(MAX_NC / 2 * 128) : static_cast<uint32_t>(MAX_NC * 128);
   static_assert((A_TILE_BYTES + W_STAGE_BYTES) % 1024 == 0, "stages stay 1024-byte aligned (SWIZZLE_128B operand atoms)");
@@ -173,12 +176,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t leader_rank = cta_rank & ~1u;   // CTA of this tcgen05 pair that issues the UMMAs and owns the barriers
-  const uint32_t pair_idx = cta_rank >> 1;
 
   if (warp == W_WARP && lane == 0) {
     for (int s = 0; s < NSTG; ++s) {
       mbar_init(bar_full(s), 2);     // weight producer + activation producer each arm their own byte count
-      mbar_init(bar_empty(s), NPAIRS);   // a stage is refilled (partly by the other pairs) once EVERY pair consumed it
+      mbar_init(bar_empty(s), 1);    // one tcgen05.commit per consumed stage
     }
     mbar_init(bar_acc_full(0), 1);
     mbar_init(bar_acc_full(1), 1);
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // dropout / bf16) -- no TMA store, no L2 round trip, no chunk barriers: the hand-off is one proxy fence and one mbarrier
   // (the peer CTA's half of the M = 256 operand is signalled through its idle UMMA warp with a cluster-scope release).  The
   // weights still stream from the L2; x_0 goes to the scratch as bf16 hi / lo and the decoder runs as in streaming mode.
-  const bool RES = PAIR && P.resident != 0;
+  constexpr bool RES = RESK;
   const uint32_t nstg = RES ? static_cast<uint32_t>(P.res_nstg) : static_cast<uint32_t>(NSTG);
   const uint32_t res_a = base_addr + nstg * STG_BYTES;
 
@@ -297,15 +299,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         if (!is_w) SDRM_TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
         const int half_rows = NC >> 1;
-        const int part_rows = NC / CS;          // rows of a weight k-block this CTA fetches (CS >= 4: multicast to its peers)
         for (int c = 0; c < NCH; ++c) {
           for (int p = 0; p < passes; ++p) {
             const int which = (p == 1) ? 1 : 0;
             const int a_buf = (p == 2) ? in_lo_buf : in_hi_buf;
             const uint8_t* a_src = sc + static_cast<size_t>(a_buf) * P.act_buf_bytes;
             const uint8_t* w_src = w_img + (static_cast<size_t>(which) * NCH + c) * KB * w_bytes;
-            int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank & 1u) * half_rows +
-                        (CS > 2 ? static_cast<int>(pair_idx) * part_rows : 0);
+            int w_row = ((which * NCH + c) * KB) * NC + static_cast<int>(cta_rank & 1u) * half_rows;
             int a_row = a_row_base + static_cast<int>((static_cast<size_t>(a_buf) * P.act_buf_bytes) >> 7);
             // resident chain layers: a stage has no activation half to fill, so it carries TWO weight k-blocks (the second in the
             // activation half): twice the weight bytes in flight -- this mode is bound by the L2 latency of the weight stream
@@ -337,12 +337,6 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     if (res_layer) {
                       tma_load_2d_pair_hint(mapa_cluster(stage_a(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
                       if (two) tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row + NC, fb0, pol_keep);
-                    } else if (CS > 2) {
-                      // this CTA's 1/CS of the k-block goes to the same smem offset of every CTA holding this N-half;
-                      // each copy completes on the full barrier of the destination's own pair leader
-                      constexpr uint16_t kHalfMask = static_cast<uint16_t>(CS == 8 ? 0x55u : 0x05u);
-                      tma_load_2d_pair_mcast_hint(stage_w(stage) + pair_idx * static_cast<uint32_t>(part_rows) * 128u, tm_w, 0, w_row,
-                                                  fb & 0xFEFFFFFFu, static_cast<uint16_t>(kHalfMask << (cta_rank & 1u)), pol_keep);
                     } else {
                       tma_load_2d_pair_hint(mapa_cluster(stage_w(stage), cta_rank), tm_w, 0, w_row, fb0, pol_keep);
                     }
@@ -398,7 +392,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         // arrive on the local barrier (CTA-scope release behind their proxy fence); this thread has no memory operation of its
         // own in flight, so its cluster-scope release costs nothing (an epilogue thread's would wait for its state stores).
         const uint32_t remote = mapa_cluster(bar_peer_ready, leader_rank);
-        const int n_layers = P.T * P.n_step;
+        const int n_layers = n_iters * P.T * P.n_step;   // (both CTAs of a pair run the same number of tile iterations)
         for (int k = 0; k < n_layers; ++k) {
           mbar_wait(bar_a_ready, static_cast<uint32_t>(k) & 1u, err, WD_RELAY);
           if (elect_one()) mbar_arrive_cluster_release(remote);
@@ -653,12 +647,30 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       }
       epi_bar_sync();
     }
-    if (RES) {   // K-padding columns of the resident tile must read as exact zeros too
+    if constexpr (RES) {   // K-padding columns of the resident tile must read as exact zeros too
       const uint32_t n16 = (static_cast<uint32_t>(NSTG) - nstg) * STG_BYTES / 16u;
       for (uint32_t i = threadIdx.x; i < n16; i += EPI_THREADS)
         asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(res_a + i * 16u), "r"(0u) : "memory");
       epi_bar_sync();
     }
+    // Lazy publication (two interleaved sub-tiles only): waiting for a chunk's TMA stores to complete right behind them costs the
+    // epilogue warps ~1.5 us per chunk (the round trip of bulk_wait_group), as much as the chunk's arithmetic.  With a second tile
+    // in between, the consumer of a chunk (the same tile's next layer) is a whole tile-layer away, so the chunk is only NOTED here
+    // and published at the start of the next chunk epilogue, when its stores have long completed.  (With one tile the next
+    // accumulator cannot become ready before the publication: prompt publication there.)
+    uint32_t pub_pend = 0;    // bit 8 s + c: chunk c of sub-tile s has been stored but not published
+    static_assert(MAX_SUB * MAX_ACT_CHUNKS <= 32 && MAX_ACT_CHUNKS == 8, "pub_pend bits");
+    auto publish_pending = [&]() {
+      if (pub_pend) {   // warp-uniform
+        stores_done();
+        if (lane0)
+          for (uint32_t m = pub_pend; m; m &= m - 1u) {
+            const uint32_t b = static_cast<uint32_t>(__ffs(m)) - 1u;
+            mbar_arrive(bar_act_chunk(b >> 3, b & 7u));
+          }
+        pub_pend = 0;
+      }
+    };
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
     uint32_t dd_cnt = 0;      // discard_done phases consumed per sub-tile (two bits each)
     // context of the sub-tile a layer works on (set_ctx): scratch pointers are recomputed, the row facts are kept per sub-tile
@@ -786,6 +798,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         float* orow = (KIND == EPI_LINEAR_OUT) ? P.logits + static_cast<size_t>(row) * P.ld_logits : nullptr;
         const bool res_layer = RES && (KIND == EPI_PRELU || KIND == EPI_POSTERIOR);   // (chain layers; the decoder streams)
         const bool publishes = !last_of_tile && KIND != EPI_LINEAR_OUT && !last_step && !res_layer;
+        const bool lazy = ns == 2;   // see publish_pending
         // The bias row is warp-uniform and read by every thread: an L1-thrashed LDG costs an L2 round trip per group.  Each
         // warp stages the 16 floats of each of its own groups of a chunk in a private shared-memory slice (lane l < 4 BIAS_SLOTS
         // holds elements 4l .. 4l+3: group slot l / 4, columns 4 (l % 4) ..) one chunk ahead, and the group loop reads them with LDS.128.
@@ -829,7 +842,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
-          if (c > 0 && c == NCH - 2 && publishes) {
+          if (lazy) {
+            publish_pending();
+          } else if (c > 0 && c == NCH - 2 && publishes) {
             // Deferred publication of ALL earlier chunks (0 .. NCH-3) with ONE proxy fence: their stores were issued at least
             // a whole accumulator wait ago, and only the next layer reads these activations -- it cannot issue its first UMMA
             // before this layer's last chunk is in the tensor pipe.  (A fence.proxy.async is a membar.gpu round trip of ~1.3 us
@@ -970,7 +985,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
           // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
-          if (publishes && c >= NCH - 2) {
+          if (publishes && lazy) {
+            pub_pend |= 1u << (8 * s + c);
+          } else if (publishes && c >= NCH - 2) {
             stores_done();
             if (lane0) mbar_arrive(bar_act_chunk(s, c));
             SDRM_TR_EPI(5);
@@ -1000,7 +1017,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = x0v[e];
               }
             }
-          if (!last_of_tile) {
+          if (!last_of_tile && lazy) {
+            pub_pend |= ((1u << NCH) - 1u) << (8 * s);
+          } else if (!last_of_tile) {
             stores_done();
             if (lane0)
               for (int c = 0; c < NCH; ++c) mbar_arrive(bar_act_chunk(s, c));
@@ -1045,6 +1064,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int s = 0; s < ns; ++s) discard_gate(s);   // the last chain layer's phase (keeps the parities in step across tiles)
       for (int l = 0; l < P.n_dec; ++l)
         for (int s = 0; s < ns; ++s) run_kind(P.dec[l], 0, l == P.n_dec - 1, P.dec[l].out_hi == 0 ? cur : cur ^ 1, P.dec[l].out_lo, s);
+      publish_pending();   // (nothing is left pending behind a decoder: its last layer publishes nothing; probe / chain-only launches)
     }
     stores_done();   // no TMA store may still be reading this CTA's shared memory at exit
   } else {

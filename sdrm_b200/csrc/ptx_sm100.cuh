@@ -154,17 +154,6 @@ __device__ __forceinline__ void tma_load_2d_pair_hint(uint32_t dst_cluster, cons
       ::"r"(dst_cluster), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster), "l"(pol)
       : "memory");
 }
-// Multicast form (clusters of several tcgen05 pairs): `dst` and `bar` are CTA-relative shared addresses applied in every CTA
-// of `cta_mask`; with .cta_group::2 and the peer bit (bit 24) of `bar` cleared, each copy signals the barrier of the
-// destination's pair LEADER.
-__device__ __forceinline__ void tma_load_2d_pair_mcast_hint(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar,
-                                                            uint16_t cta_mask, uint64_t pol) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
-      " [%0], [%1, {%2, %3}], [%4], %5, %6;"
-      ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask), "l"(pol)
-      : "memory");
-}
 // 2-D tensor-map load into this CTA's shared memory, completion on a local mbarrier (single-CTA mode)
 __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar, uint64_t pol) {
   asm volatile(

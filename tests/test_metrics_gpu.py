@@ -77,6 +77,14 @@ def test_topk_pooled_kernel_worst_cases(k):
     x[1, 100:164] = x[1, 2400]                     # a run of ties inside an ascending row
     got = metrics.topk_device(torch.from_numpy(x).cuda(), k).cpu().numpy()
     assert np.array_equal(got, np.argsort(-x, axis=1, kind="stable")[:, :k])
+    z = rng.randn(5, 900).astype(np.float32)       # signed zeros are EQUAL scores (ties -> lower index), denormals are not zero
+    z[:, ::3] = 0.0
+    z[:, 1::6] = -0.0
+    z[:, 2::9] = np.float32(1e-42)
+    z[:, 5::11] = np.float32(-1e-42)
+    z[2] = np.where(np.arange(900) % 2 == 0, np.float32(-0.0), np.float32(0.0))
+    got = metrics.topk_device(torch.from_numpy(z).cuda(), k).cpu().numpy()
+    assert np.array_equal(got, np.argsort(-z, axis=1, kind="stable")[:, :k])
     xd = rng.randn(9, 1777)                        # float64, odd width (scalar tail loads)
     xd[:, 300] = xd[:, 900] + 1e-13
     got = metrics.topk_device(torch.from_numpy(xd).cuda(), k).cpu().numpy()

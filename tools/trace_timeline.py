@@ -11,6 +11,8 @@ diff, vae = build_models(w, "cuda")
 eng = engine_for(diff, "cuda")   # needs a -DSDRM_TRACE (and, for the flags, -DSDRM_PERF_DEBUG) build selected with SDRM_B200_LIB
 eng.set_option(_lib.OPT_CLUSTER, int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 eng.set_option(_lib.OPT_DEBUG_FLAGS, int(os.environ.get('SDRM_DEBUG_FLAGS', '0')))
+eng.set_option(_lib.OPT_SUBTILES, int(os.environ.get('SDRM_SUBTILES', '0')))
+eng.set_option(_lib.OPT_RESIDENT, int(os.environ.get('SDRM_NO_RESIDENT', '0')))
 CAP = 8192
 buf = torch.zeros(3 * CAP, dtype=torch.int64, device="cuda")
 out = sample_ddpm(rows, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=1)

@@ -684,11 +684,20 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   }
   // Sub-tiles: a pair that owns two or more row tiles interleaves two of them layer by layer (see the kernel)
   const long long n_local = (n_tiles + launch_grid - 1) / launch_grid;
-  // (measured on B200 at cfg 5: the second tile doubles the L2-resident scratch of a CTA, the L2 hit rate drops from 80 % to
-  // 67 %, DRAM traffic grows by half and the shard takes 309.6 instead of 295.6 ms; so the default stays one tile and the
-  // interleave is an opt-in for shapes whose scratch fits the L2)
+  // Which of the three data flows a pair-mode launch takes (all bit-identical), measured on B200 with tools/shape_probe.py:
+  //   * two interleaved sub-tiles per CTA (streaming through the L2): narrow denoisers with several tiles per CTA.  A layer's UMMAs
+  //     are short there and the hand-off of a tile's layer hides behind the other tile's work: L = 96 / 128 / 200 / 264 / 300 at
+  //     80 000 - 150 000 users: +21 / +18 / +10 / +6.5 / +2.5 % over the best single-tile flow.  From ~320 columns on it loses (the
+  //     second tile doubles the scratch and the L2 traffic: cfg-2 widths -5 %, cfg 5 -8 % with the L2 hit rate down from 80 to 67 %);
+  //   * resident mode (below): everything else that fits it, except one-tile-per-CTA launches of very narrow denoisers (<= 128
+  //     columns: 0.798 vs 0.824 ms, the tile hand-off through the L2 is as fast and the weight stream keeps all 6 stages);
+  //   * one streaming tile per CTA: the wide denoisers (cfg 1, cfg 5).
+  int w_max = 0;
+  for (int j = 0; j < P.n_step; ++j) w_max = std::max(w_max, std::max(P.step[j].KB * KBLK, P.step[j].NCH * P.step[j].NC));
   P.n_sub = 1;
-  if (h->subtile_override == 2 && cluster >= 2 && n_local >= 2) P.n_sub = 2;
+  if (cluster == 2 && n_local >= 2 && P.n_step > 0 &&
+      (h->subtile_override == 2 || (h->subtile_override == 0 && w_max <= 320)))
+    P.n_sub = 2;
   // Dead-buffer discard (pair mode, see the kernel's discard warp): whole k-blocks of a chain layer's input image that EVERY
   // chain layer's epilogue rewrites completely (64-column blocks below the narrowest written width), so a partly written
   // last k-block keeps the zero padding it got at kernel start.
@@ -704,7 +713,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // (~9 TB/s of activation re-reads, weights, stores and state at 148 CTAs), and the resident tile removes the activation half of it
   // (cfg-2 widths, 100 000 users: 14.91 -> 14.39 ms; cfg-4 widths, 60 000 users: 5.55 -> 5.26 ms).
   P.resident = 0; P.res_nstg = 0;
-  if (cluster == 2 && P.n_sub == 1 && P.n_step > 0 && h->no_resident != 1) {
+  if (cluster == 2 && P.n_sub == 1 && P.n_step > 0 && h->no_resident != 1 && (n_local >= 2 || w_max > 128)) {
     int kb_max = 0;
     bool ok = true;
     for (int j = 0; j < P.n_step; ++j) {

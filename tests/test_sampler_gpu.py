@@ -119,30 +119,35 @@ def test_single_and_pair_mode_are_bit_identical():
 def test_resident_mode_is_bit_identical_to_streaming(shape):
     """Pair-mode launches of denoisers up to 512 wide keep the chain's activation tile in shared memory (resident mode), with
     one row tile per CTA or several in sequence (grid cap); SDRM_OPT_RESIDENT = 1 forces the L2-streaming path.  Same
-    arithmetic, same rows."""
+    arithmetic, same rows.  (Automatic choice, engine_host.cu: one tile per CTA -> resident above 128 columns; several tiles per
+    CTA -> two interleaved streaming sub-tiles up to 320 columns, resident above.)"""
     from sdrm_b200 import _lib
     lib = _lib.load()
     n, I, H, L, T, nh = shape
+    w = max((L + 63) // 64 * 64, (L + 15) // 16 * 16 if L <= 256 else 2 * (((L + 1) // 2 + 15) // 16 * 16))
+    fits = L <= 512
     diff, vae = random_modules(I, H, L, T, nh, seed=11, device="cuda")
     eng = _engine(diff, vae, T, 1.0)
-    lat_a = torch.empty(n, L, device="cuda")
-    lat_b = torch.empty(n, L, device="cuda")
-    a = eng.sample(n, seed=5, latent_out=lat_a, check=True).clone()
-    assert lib.sdrm_last_resident_mode(eng.handle) == (1 if L <= 512 else 0)
+    lat = [torch.empty(n, L, device="cuda") for _ in range(4)]
     try:
+        a = eng.sample(n, seed=5, latent_out=lat[0], check=True).clone()
+        assert lib.sdrm_last_resident_mode(eng.handle) == (1 if fits and w > 128 else 0)
         eng.set_option(_lib.OPT_RESIDENT, 1)
-        b = eng.sample(n, seed=5, latent_out=lat_b, check=True)
+        b = eng.sample(n, seed=5, latent_out=lat[1], check=True).clone()
         assert lib.sdrm_last_resident_mode(eng.handle) == 0
         eng.set_option(_lib.OPT_RESIDENT, 0)
-        eng.set_option(_lib.OPT_GRID_LIMIT, 4)          # two pairs: every CTA runs several row tiles one after the other
-        lat_c = torch.empty(n, L, device="cuda")
-        c = eng.sample(n, seed=5, latent_out=lat_c, check=True)
-        assert lib.sdrm_last_resident_mode(eng.handle) == (1 if L <= 512 else 0)
+        eng.set_option(_lib.OPT_GRID_LIMIT, 4)          # two pairs: every CTA runs several row tiles
+        c = eng.sample(n, seed=5, latent_out=lat[2], check=True).clone()   # automatic: sub-tiles or resident by width
+        assert lib.sdrm_last_resident_mode(eng.handle) == (1 if fits and w > 320 else 0)
+        eng.set_option(_lib.OPT_SUBTILES, 1)            # one tile at a time: resident whenever it fits
+        d = eng.sample(n, seed=5, latent_out=lat[3], check=True)
+        assert lib.sdrm_last_resident_mode(eng.handle) == (1 if fits else 0)
     finally:
         eng.set_option(_lib.OPT_RESIDENT, 0)
         eng.set_option(_lib.OPT_GRID_LIMIT, 0)
-    assert torch.equal(a, b) and torch.equal(lat_a, lat_b)
-    assert torch.equal(a, c) and torch.equal(lat_a, lat_c)
+        eng.set_option(_lib.OPT_SUBTILES, 0)
+    for o, l_ in ((b, lat[1]), (c, lat[2]), (d, lat[3])):
+        assert torch.equal(a, o) and torch.equal(lat[0], l_)
 
 
 def test_interleaved_sub_tiles_are_bit_identical():

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
-  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 2;   // mbarriers of a CTA (map below)
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 3;   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
   constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // memory; peer_ready (leader's copy) = the same for the peer CTA, relayed by the peer's otherwise idle UMMA warp
   const uint32_t bar_a_ready = bar_base + 8u * (3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6));
   const uint32_t bar_peer_ready = bar_a_ready + 8u;
+  // resident mode, two-chunk layers: the second chunk's UMMAs have read the k-blocks that the FIRST chunk's output overwrites
+  const uint32_t bar_half_read = bar_a_ready + 16u;
   // per-role layer counters: two bits per sub-tile (k mod 4 is all the ring index and the parity need)
   auto cnt_get = [](uint32_t cnt, int s) -> uint32_t { return (cnt >> (2 * s)) & 3u; };
   auto cnt_inc = [](uint32_t cnt, int s) -> uint32_t { return (cnt & ~(3u << (2 * s))) | ((((cnt >> (2 * s)) + 1u) & 3u) << (2 * s)); };
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_tile_ready, EPI_WARPS);
     mbar_init(bar_a_ready, EPI_WARPS);
     mbar_init(bar_peer_ready, 1);
+    mbar_init(bar_half_read, 1);
     fence_mbar_init();
   }
   if (warp == M_WARP) {
@@ -415,6 +418,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           const int KB = ldref.KB, NCH = ldref.NCH, passes = ldref.passes, kmma_last = ldref.kmma_last;
           const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, ldref.NC);
           const bool res_layer = RES && chain;
+          const int half_kb = (ldref.NC - 1) >> 6;   // last k-block under the first chunk's output columns
           if (res_layer) {
             // both halves of the M = 256 input tile are in place (and the previous layer's accumulators have been read)
             mbar_wait(bar_a_ready, a_par, err, WD_MMA_AREADY);
@@ -456,6 +460,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     if (nk2 > 2) umma_bf16_ss_pair(d_tmem, a2 + 4u, b2 + 4u, idesc, 1u);
                     if (nk2 > 3) umma_bf16_ss_pair(d_tmem, a2 + 6u, b2 + 6u, idesc, 1u);
                     umma_commit_pair(bar_empty(stage), static_cast<uint16_t>((1u << CS) - 1u));
+                    // two-chunk layer, second chunk: once the k-blocks under the first chunk's output columns have been read
+                    // (by BOTH chunks: a commit covers every earlier UMMA) the epilogue may overwrite them -- the first chunk's
+                    // epilogue then runs in the shadow of the rest of this chunk
+                    if (NCH == 2 && c == 1 && kb <= half_kb && half_kb <= kb + 1)
+                      umma_commit_pair(bar_half_read, static_cast<uint16_t>(0x3u << leader_rank));
                   } else if (PAIR) {
                     umma_bf16_ss_pair(d_tmem, a_desc, b_desc, idesc, acc);
                     if (nk > 1) umma_bf16_ss_pair(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
@@ -671,6 +680,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         pub_pend = 0;
       }
     };
+    uint32_t half_par = 0;    // parity of bar_half_read (resident mode, two-chunk layers)
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
     uint32_t dd_cnt = 0;      // discard_done phases consumed per sub-tile (two bits each)
     // context of the sub-tile a layer works on (set_ctx): scratch pointers are recomputed, the row facts are kept per sub-tile
@@ -808,12 +818,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           return (lane < 4 * BIAS_SLOTS && slice_g < ngroups) ? *reinterpret_cast<const float4*>(bias_row + c * NC + slice_o) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         float4 bnext = fetch_slice(0);
-        if (res_layer) {
-          // the layer's output overwrites its own input tile: every UMMA of the layer (all chunks) must have retired first.
-          // (A parity wait does not consume the phase: the chunk loop below waits for the same phases again and falls through.)
-          const uint32_t cl = cc + static_cast<uint32_t>(NCH) - 1u;
-          mbar_wait(bar_acc_full(cl & 1u), (cl >> 1) & 1u, err, WD_EPI_LAYER);
-        }
+        // Resident layer: the output overwrites the layer's own input tile.  One chunk: its accumulator is complete, so every UMMA
+        // has retired.  Two chunks: the first chunk's epilogue starts as soon as ITS accumulator is complete and only waits, before
+        // its first store, until the second chunk's UMMAs have read the k-blocks under its columns (bar_half_read) -- it runs in
+        // the shadow of the rest of the second chunk.
         for (int c = 0; c < NCH; ++c) {
           const uint32_t buf = cc & 1u;
           const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
@@ -858,6 +866,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
           if (KIND == EPI_POSTERIOR && c > 0 && sub < ngroups) request_state(sub);
+          if (res_layer && NCH == 2 && c == 0) {   // (before the TMEM load: with the accumulator registers live across a wait ptxas spills)
+            mbar_wait(bar_half_read, half_par, err, WD_EPI_LAYER);
+            half_par ^= 1u;
+          }
           if (sub < ngroups) tmem_ld16(t_chunk + sub * 16u, v);
           const float4* bs = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll 1

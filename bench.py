@@ -395,6 +395,12 @@ def run_ours(args, w, rank, world, local_rank):
             rows = args.cpu_rows or max(64, min(4096, int(2.0e12 / F)))
             rate, dt, kind = cpu_reference_rate(w, rows, threads)
             cpu = {"value": rate, "unit": "users/s", "cores": threads, "kind": kind, "seconds": dt, "sample": _cpu_sample_text(kind, rows, w)}
+        secondary = None
+        if world == 1 and not args.no_secondary:
+            try:
+                secondary = secondary_kernels(args, w, dev, diff, vae, out, peaks)
+            except Exception as exc:   # the headline line must survive a failure of the side measurements
+                secondary = {"error": repr(exc)[:200]}
         line = {
             "metric": "synthetic users/sec (full reverse diffusion + decode)", "value": value, "unit": "users/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -405,12 +411,70 @@ def run_ours(args, w, rank, world, local_rank):
                        "l2": "each step writes n*I*4 bytes of logits (>> 126 MB L2 for cfg5); no reuse across steps",
                        "precision": "bf16 operands / fp32 accumulate in the chain, bf16x3 split in the decoder"},
             "clocks": clock_info, "e2e": e2e, "cluster": int(eng.lib.sdrm_last_cluster_size(eng.handle)), "resident": int(eng.lib.sdrm_last_resident_mode(eng.handle)), "subtiles": args.subtiles, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "secondary": secondary,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
 
+
+
+def secondary_kernels(args, w, dev, diff, vae, out, peaks):
+    """The other kernels of the path, timed in the same process on the logits the timed steps left in `out` (rank 0, one GPU):
+    multi-resolution sampling (train_SDRM.py:37-49), K3 top-k (utilities.py:149-171), K4 equal-sparsity binarisation
+    (main.py:177-185) and K2 forward noising (train_SDRM.py:191-199).  CUDA events, 3 repetitions after one warm-up, best."""
+    import numpy as np
+    import torch
+    from sdrm_b200 import metrics
+    from sdrm_b200.sparsify import equal_sparsity_device
+    from sdrm_b200.train_SDRM import sample_ddpm
+    from sdrm_b200.training import CudaLossBackend
+
+    def best_ms(fn, reps=3):
+        fn()
+        ms = []
+        for _ in range(reps):
+            torch.cuda.synchronize(dev)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize(dev)
+            ms.append(a.elapsed_time(b))
+        return min(ms)
+
+    res = {}
+    n, I = out.shape
+    # multi-resolution mode: row j runs t_j ~ U{1..T-1} steps (single-CTA tiles, rows sorted by chain length)
+    n_r = min(n, 148 * 128)
+    np.random.seed(0)
+    ms = best_ms(lambda: sample_ddpm(n_r, diff, vae, w["L"], w["nd"], timesteps="random", n_timesteps=w["T"], seed=5, out=out[:n_r], reuse_packed=True))
+    res["sample_ddpm_random"] = {"users_per_s": n_r / (ms * 1e-3), "ms": ms, "rows": n_r, "note": "timesteps='random': mean chain length T/2, one 128-row tile per CTA"}
+    # refill `out` with full-resolution logits for the score consumers below
+    sample_ddpm(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=6, out=out, reuse_packed=True)
+    # (the chain kernel leaves the board at its power cap with the SM clock near 1.2 GHz; the HBM-bound kernels below are timed
+    # after a pause, i.e. at the clocks they see when they are not queued right behind 280 ms of tensor work)
+    torch.cuda.synchronize(dev)
+    time.sleep(1.0)
+    rows = min(n, 65536)
+    for k in (10, 50):
+        ms = best_ms(lambda: metrics.topk_device(out[:rows], k))
+        gbs = 4.0 * rows * I / (ms * 1e-3) / 1e9
+        res[f"topk_k{k}"] = {"ms": ms, "GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "rows": rows, "items": I}
+    ms = best_ms(lambda: equal_sparsity_device(out, 0.99))
+    res["equal_sparsity_pack"] = {"ms": ms, "rows": n, "items": I, "passes_GBps": 4.0 * 4.0 * n * I / (ms * 1e-3) / 1e9,
+                                  "note": "3 radix-select histogram passes + threshold/pack pass over the fp32 scores, end to end incl. the device walk"}
+    # K2: forward noising of a [B, L] latent minibatch (1 read, 4 writes)
+    B = 262144
+    mu = torch.randn(B, w["L"], device=dev)
+    t = torch.randint(1, w["T"] + 1, (B,), device=dev)
+    from sdrm_b200.models import make_schedule
+    _, _, ab_t = make_schedule(w["T"], device=dev)
+    be = CudaLossBackend()
+    ms = best_ms(lambda: be.noise_inputs(mu, t, ab_t, w["nd"], 0.1, 11, 0))
+    gbs = 5.0 * 4.0 * B * w["L"] / (ms * 1e-3) / 1e9
+    res["noise_inputs"] = {"ms": ms, "GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "rows": B, "L": w["L"]}
+    return res
 
 
 def train_flops_per_row(w):
@@ -558,6 +622,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the side measurements (random mode, K3, K4, K2) of the default run")
     ap.add_argument("--no-eager", action="store_true", help="--impl reference: skip the eager-CUDA run of the reference")
     ap.add_argument("--eager-rows", type=int, default=None, help="--impl reference: rows of the eager-CUDA sample")
     ap.add_argument("--cluster", type=int, default=0, help="force single CTAs (1) or tcgen05 CTA pairs (2); 0 = auto")

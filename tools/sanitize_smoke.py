@@ -1,4 +1,5 @@
-"""Small launches of every kernel family for `compute-sanitizer --tool memcheck python tools/sanitize_smoke.py` (out-of-bounds check)."""
+"""Small launches of every kernel family and data flow in one process (a quick smoke after kernel edits; also the script to
+put under `compute-sanitizer --tool memcheck` where the pool allows it)."""
 import os
 import sys
 

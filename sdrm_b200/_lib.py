@@ -28,6 +28,7 @@ SIGNATURES = {
     "sdrm_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
     "sdrm_last_cluster_size": (C.c_int, [_P]),
     "sdrm_last_resident_mode": (C.c_int, [_P]),
+    "sdrm_last_split_size": (C.c_int, [_P]),
     "sdrm_resident_ctas": (C.c_int, [_P, C.c_int]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "sdrm_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),
@@ -60,7 +61,7 @@ SIGNATURES = {
 }
 
 
-OPT_CLUSTER, OPT_SUBTILES, OPT_GRID_LIMIT, OPT_NO_DISCARD, OPT_ENGINE, OPT_RESIDENT, OPT_DEBUG_FLAGS, OPT_TRACE_BUFFER = 1, 2, 3, 4, 5, 6, 100, 101   # enum sdrm_option
+OPT_CLUSTER, OPT_SUBTILES, OPT_GRID_LIMIT, OPT_NO_DISCARD, OPT_ENGINE, OPT_RESIDENT, OPT_NO_SPLIT, OPT_DEBUG_FLAGS, OPT_TRACE_BUFFER = 1, 2, 3, 4, 5, 6, 7, 100, 101   # enum sdrm_option
 
 
 class SdrmError(RuntimeError):

@@ -204,6 +204,9 @@ struct sdrm_handle {
   int subtile_override = 0;     // 1 / 2 row tiles a CTA interleaves
   int no_discard = 0;           // 1 = keep dead activation lines in the L2 (A/B of the discard warp)
   int no_resident = 0;          // 1 = never keep the chain's activation tile in shared memory (A/B of the resident mode)
+  int no_split = 0;             // 1 = never split a row tile's N chunks over a cluster (A/B of the column-split mode)
+  int split_resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // resident CTAs of the column-split kernel per cluster size (2, 4, 8)
+  int last_split = 0;           // cluster size of the last launch's column split (0: not split)
   int last_resident = 0;        // what the last sdrm_sample launch did
   int grid_limit = 0;           // cap on the CTAs of an sdrm_sample launch (tests: small inputs exercise the multi-tile loops)
   int debug_flags = 0;          // -DSDRM_PERF_DEBUG builds only
@@ -271,12 +274,13 @@ static int engine_set_smem_attr() {
   SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   SDRM_CUDA(cudaFuncSetAttribute(sdrm_layer_engine_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   SDRM_CUDA(cudaFuncSetAttribute((sdrm_layer_engine_kernel<2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
+  SDRM_CUDA(cudaFuncSetAttribute((sdrm_layer_engine_kernel<1, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, ENGINE_SMEM_BYTES));
   if (dev < 64) done[dev] = true;
   return SDRM_OK;
 }
 
 // resident CTAs for a cluster size (1 CTA per SM; clusters must fit inside a GPC)
-static int max_resident_ctas(int cluster, int num_sms) {
+static int max_resident_ctas(int cluster, int num_sms, bool split = false) {
   if (cluster == 1) return num_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(num_sms / cluster * cluster));
@@ -287,8 +291,9 @@ static int max_resident_ctas(int cluster, int num_sms) {
   attr.val.clusterDim.x = cluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
   cfg.attrs = &attr; cfg.numAttrs = 1;
   int n = 0;
-  if (cluster != 2) return 0;
-  cudaError_t e = cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<2>, &cfg);
+  if (!split && cluster != 2) return 0;
+  cudaError_t e = split ? cudaOccupancyMaxActiveClusters(&n, (sdrm_layer_engine_kernel<1, false, true>), &cfg)
+                        : cudaOccupancyMaxActiveClusters(&n, sdrm_layer_engine_kernel<2>, &cfg);
   if (e != cudaSuccess) { cudaGetLastError(); return 0; }
   return n * cluster;
 }
@@ -352,7 +357,20 @@ static int fill_pair_maps(ChainParams& P, size_t workspace_bytes, int cluster) {
   return SDRM_OK;
 }
 
-static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st) {
+static int launch_engine(const ChainParams& P, int grid, int cluster, cudaStream_t st, int split = 0) {
+  if (split > 1) {   // column-split mode: single-CTA tiles, a cluster of `split` CTAs per row tile
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(ENGINE_THREADS);
+    cfg.dynamicSmemBytes = ENGINE_SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = split; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    SDRM_CUDA(cudaLaunchKernelEx(&cfg, (sdrm_layer_engine_kernel<1, false, true>), P));
+    return SDRM_OK;
+  }
   if (cluster == 1) {
     sdrm_layer_engine_kernel<1><<<grid, ENGINE_THREADS, ENGINE_SMEM_BYTES, st>>>(P);
     SDRM_CUDA(cudaGetLastError());
@@ -412,6 +430,7 @@ int sdrm_create(sdrm_handle** out, int device) {
   if (engine_set_smem_attr() != SDRM_OK) { delete h; return SDRM_ERR_CUDA; }
   h->resident[1] = h->num_sms;
   h->resident[2] = max_resident_ctas(2, h->num_sms);
+  for (int cs = 2; cs <= 8; cs *= 2) h->split_resident[cs] = max_resident_ctas(cs, h->num_sms, true);
   *out = h;
   return SDRM_OK;
 }
@@ -665,7 +684,23 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // multi-resolution chains (per-tile step counts) and single-tile calls use single-CTA mode
   if (d_t_start == nullptr && n_tiles >= 2) cluster = 2;
   if (h->cluster_override > 0 && (d_t_start == nullptr || h->cluster_override == 1)) cluster = h->cluster_override;
+  // Column-split mode (see the kernel): full-resolution chains of a FEW row tiles of a WIDE denoiser (3 - 8 N chunks per chain
+  // layer, i.e. wider than the resident flow takes): a cluster of S = 4 / 8 CTAs per tile, CTA j computes the chunks c = j (mod S).
+  // One tile per cluster, all clusters resident at once.
+  int split = 0;
+  {
+    int nch_min = MAX_ACT_CHUNKS, nch_max = 0;
+    for (int j = 0; j < P.n_step; ++j) { nch_min = std::min(nch_min, P.step[j].NCH); nch_max = std::max(nch_max, P.step[j].NCH); }
+    if (d_t_start == nullptr && P.n_step > 0 && !h->no_split && nch_min >= 3 && (h->cluster_override == 0 || h->cluster_override >= 4)) {
+      int S = nch_max <= 4 ? 4 : 8;
+      if (h->cluster_override >= 4) S = h->cluster_override;
+      if (h->split_resident[S] > 0 && n_tiles * S <= h->split_resident[S] && (h->grid_limit == 0 || n_tiles * S <= h->grid_limit)) split = S;
+    }
+  }
+  h->last_split = split;
   int launch_grid = 0;
+  if (split) { cluster = 1; launch_grid = static_cast<int>(n_tiles) * split; }
+  else
   for (; cluster >= 1; cluster >>= 1) {
     const int resident = h->resident[cluster];
     if (resident <= 0) continue;
@@ -674,7 +709,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     if (h->grid_limit > 0) launch_grid = std::min(launch_grid, std::max(cluster, h->grid_limit / cluster * cluster));
     break;
   }
-  if (launch_grid <= 0 || launch_grid > grid) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
+  if (launch_grid <= 0 || (split ? n_tiles > grid : launch_grid > grid)) return sdrm_fail(SDRM_ERR_CUDA, "sdrm_sample: no launchable grid");
   h->last_cluster = cluster;
   rc = fill_act_maps(P, static_cast<size_t>(grid) * stride);
   if (rc) return rc;
@@ -683,7 +718,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     if (rc) return rc;
   }
   // Sub-tiles: a pair that owns two or more row tiles interleaves two of them layer by layer (see the kernel)
-  const long long n_local = (n_tiles + launch_grid - 1) / launch_grid;
+  const long long n_local = split ? 1 : (n_tiles + launch_grid - 1) / launch_grid;
   // Which of the three data flows a pair-mode launch takes (all bit-identical), measured on B200 with tools/shape_probe.py:
   //   * two interleaved sub-tiles per CTA (streaming through the L2): narrow denoisers with several tiles per CTA.  A layer's UMMAs
   //     are short there and the hand-off of a tile's layer hides behind the other tile's work: L = 96 / 128 / 200 / 264 / 300 at
@@ -728,9 +763,9 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     }
   }
   h->last_resident = P.resident;
-  if (static_cast<size_t>(launch_grid) * P.n_sub * stride > workspace_bytes)
+  if (static_cast<size_t>(split ? n_tiles : launch_grid) * P.n_sub * stride > workspace_bytes)
     return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small for the sub-tile scratch slots");
-  rc = launch_engine(P, launch_grid, cluster, st);
+  rc = launch_engine(P, launch_grid, cluster, st, split);
   if (rc) return rc;
   h->last_launches = 1;
   return SDRM_OK;
@@ -738,6 +773,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
 
 int sdrm_last_launch_count(const sdrm_handle* h) { return h ? h->last_launches : 0; }
 int sdrm_last_resident_mode(const sdrm_handle* h) { return h ? h->last_resident : 0; }
+int sdrm_last_split_size(const sdrm_handle* h) { return h ? h->last_split : 0; }
 
 int sdrm_check_device_error(sdrm_handle* h, void* stream) {
   if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "null handle");
@@ -770,8 +806,11 @@ int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
   if (!h) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: null handle");
   const int v = static_cast<int>(value);
   switch (option) {
+    case SDRM_OPT_NO_SPLIT:
+      h->no_split = v != 0;
+      return SDRM_OK;
     case SDRM_OPT_CLUSTER:
-      if (!(v == 0 || v == 1 || v == 2)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: cluster must be 0 (automatic), 1 or 2");
+      if (!(v == 0 || v == 1 || v == 2 || v == 4 || v == 8)) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_set_option: cluster must be 0 (automatic), 1, 2, or 4 / 8 (column split)");
       h->cluster_override = v;
       return SDRM_OK;
     case SDRM_OPT_SUBTILES:

@@ -112,9 +112,11 @@ __device__ __forceinline__ void xs_store16(float* xs, int g16, int r, const floa
 //               (profiles/k1_bound_r02.txt): the kernel is bound by board power, not by L2 -> SM bytes.  Pruned.)
 // RESK: the resident-mode instantiation (see below).  A template parameter, not a run-time flag: the streaming instantiation must not
 // carry the mode's branches in the single-thread UMMA issue loop and in the epilogue group loops (measured: +1.2 % per cfg-5 shard).
-template <int CS, bool RESK = false>
+// SPLITK: the column-split instantiation (see below): single-CTA tcgen05, a CLUSTER of 2 / 4 / 8 CTAs shares one row tile.
+template <int CS, bool RESK = false, bool SPLITK = false>
 __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(const __grid_constant__ ChainParams P) {
   static_assert(!RESK || CS == 2, "resident mode runs on CTA pairs");
+  static_assert(!SPLITK || CS == 1, "column-split clusters are built from single-CTA (cta_group::1) tiles");
   static_assert(CS == 1 || CS == 2, "single CTAs or one tcgen05 pair per cluster");
   constexpr bool PAIR = CS == 2;
   constexpr int NSTG = PAIR ? SDRM_NSTG_PAIR : 4;
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
-  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 3;   // mbarriers of a CTA (map below)
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 5;   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
   constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -164,6 +166,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t bar_peer_ready = bar_a_ready + 8u;
   // resident mode, two-chunk layers: the second chunk's UMMAs have read the k-blocks that the FIRST chunk's output overwrites
   const uint32_t bar_half_read = bar_a_ready + 16u;
+  // column-split mode: epilogue warps -> relay warp ("this CTA's chunk of the layer's output is in the L2"), a ring of two
+  auto bar_relay = [&](uint32_t k) { return bar_a_ready + 24u + 8u * (k & 1u); };
   // per-role layer counters: two bits per sub-tile (k mod 4 is all the ring index and the parity need)
   auto cnt_get = [](uint32_t cnt, int s) -> uint32_t { return (cnt >> (2 * s)) & 3u; };
   auto cnt_inc = [](uint32_t cnt, int s) -> uint32_t { return (cnt & ~(3u << (2 * s))) | ((((cnt >> (2 * s)) + 1u) & 3u) << (2 * s)); };
@@ -178,6 +182,24 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t leader_rank = cta_rank & ~1u;   // CTA of this tcgen05 pair that issues the UMMAs and owns the barriers
+  // Column-split mode (SPLIT): the latency regime of WIDE denoisers (a handful of row tiles, chain layers of 3 - 8 N chunks: the
+  // ml-100k configuration has 7 tiles of 830 columns).  One SM per tile spends a layer's whole N x K on ONE tensor core while 140 SMs
+  // idle, and the resident flow does not fit (tile > shared memory, N > 512 TMEM columns).  Here a cluster of S = 2 / 4 / 8 CTAs owns
+  // ONE row tile: CTA j computes the N chunks c = j (mod S) of every layer over the full K -- it streams the whole activation image
+  // and only its own chunks' weights -- and owns the same columns of the fp32 state, the keep bits and the noise.  Activations
+  // still travel through the tile's scratch in the L2 (TMA store -> TMA load), but the chunk barriers now span the cluster: a
+  // CTA's epilogue warps arrive on a local relay barrier once their TMA stores have completed, and the otherwise idle fourth
+  // control warp forwards ONE cluster-scope release arrival per chunk to the chunk barrier of every CTA of the cluster (an
+  // epilogue thread's own cluster-scope release would first drain its outstanding fp32 state stores).  The chunk barriers are a
+  // ring of two per chunk index (layer parity): a CTA can finish layer l + 1 before a slow peer has consumed layer l's
+  // phases, but not layer l + 2 (that needs the peer's chunk of layer l + 1).  One tile per cluster, full-resolution chains only.
+  constexpr bool SPLIT = SPLITK;
+  const uint32_t split_n = SPLIT ? cluster_nctarank() : 1u;
+  const uint32_t split_rank = SPLIT ? cluster_ctarank() : 0u;
+  // this CTA's chunks of a layer: c = c_first, c_first + c_step, ...  (macros over the special registers, NOT variables: the
+  // epilogue's group loops have no register to spare for two more loop invariants; 0 and 1 at compile time without the split)
+#define c_first (SPLIT ? static_cast<int>(cluster_ctarank()) : 0)
+#define c_step (SPLIT ? static_cast<int>(cluster_nctarank()) : 1)
 
   if (warp == W_WARP && lane == 0) {
     for (int s = 0; s < NSTG; ++s) {
@@ -189,7 +211,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_acc_empty(0), EPI_WARPS * (PAIR ? 2 : 1));   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
     mbar_init(bar_acc_empty(1), EPI_WARPS * (PAIR ? 2 : 1));
     for (int s = 0; s < MAX_SUB; ++s) {
-      for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), EPI_WARPS);
+      for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), SPLIT ? 1 : EPI_WARPS);   // (split: one relayed arrival)
       mbar_init(bar_state_ready(s), EPI_WARPS);
       mbar_init(bar_noise_ready(s), NOISE_WARPS);
       for (uint32_t k = 0; k < 2; ++k) {
@@ -201,15 +223,27 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_a_ready, EPI_WARPS);
     mbar_init(bar_peer_ready, 1);
     mbar_init(bar_half_read, 1);
+    mbar_init(bar_relay(0), EPI_WARPS);
+    mbar_init(bar_relay(1), EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == M_WARP) {
     if (PAIR) { tmem_alloc_pair(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish_pair(); }
     else { tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512); tmem_relinquish(); }
   }
+  if constexpr (SPLIT) {
+    // the tile's activation buffers are shared by the cluster: every CTA zeroes its slice (K-padding columns must read as exact
+    // zeros) before ANY CTA may store into them -- the cluster barrier below orders it
+    uint4* z = reinterpret_cast<uint4*>(P.scratch + static_cast<size_t>(blockIdx.x / split_n) * P.scratch_stride);
+    const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
+    for (size_t i = static_cast<size_t>(split_rank) * ENGINE_THREADS + threadIdx.x; i < n16; i += static_cast<size_t>(split_n) * ENGINE_THREADS)
+      z[i] = make_uint4(0, 0, 0, 0);
+    __threadfence();
+    fence_proxy_async();   // read by TMA loads, partly overwritten by TMA stores
+  }
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anyone commits / arrives remotely
+  if (PAIR || SPLIT) cluster_sync_all();   // the peer's barriers exist before anyone commits / arrives remotely
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Resident mode (pair mode, every CTA owns ONE row tile: the dataset-sized configurations, where a layer's latency and not
@@ -225,10 +259,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t res_a = base_addr + nstg * STG_BYTES;
 
   const long long n_tiles = (P.n_rows + TILE_M - 1) / TILE_M;
-  const long long n_clusters = gridDim.x / NCTA;
-  const long long my_cluster = blockIdx.x / NCTA;
+  const long long n_clusters = SPLIT ? gridDim.x / split_n : gridDim.x / NCTA;
+  const long long my_cluster = SPLIT ? blockIdx.x / split_n : blockIdx.x / NCTA;
   // both CTAs of a pair run the same number of tile iterations (a ghost tile past n_tiles has no valid row)
-  const int n_local = static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);   // row tiles of this CTA
+  const int n_local = SPLIT ? static_cast<int>((n_tiles + n_clusters - 1) / n_clusters)
+                            : static_cast<int>((n_tiles + gridDim.x - 1) / gridDim.x);   // row tiles of this CTA (split: of this cluster)
   // Sub-tiles: an iteration works on NSUB = P.n_sub (1 or 2) row tiles at once and INTERLEAVES them layer by layer
   // (step i: layer 0 of tile 0, layer 0 of tile 1, layer 1 of tile 0, ...).  A layer's first chunk needs the last chunk
   // of the previous layer of the SAME tile out of its epilogue (stores + proxy fence + TMA round trip: the tensor pipe
@@ -255,7 +290,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 #endif
 
   auto scratch_of = [&](long long tile, int s) -> uint8_t* {
-    const long long idx = P.preloaded_input ? tile : static_cast<long long>(blockIdx.x) * NSUB + s;
+    const long long idx = P.preloaded_input ? tile : SPLIT ? my_cluster : static_cast<long long>(blockIdx.x) * NSUB + s;
     return P.scratch + static_cast<size_t>(idx) * P.scratch_stride;
   };
 
@@ -283,6 +318,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       // kb only needs the chunks covering features < 64 (kb + 1), so a layer starts while the previous layer's last
       // chunk is still in its epilogue.
       int prev_nch = 0, prev_nc = 1;
+      uint32_t lk = 0;   // layers of this tile so far (split mode: the chunk-barrier ring is indexed by its low bit)
+      if (SPLIT) {       // x_T and the first input image are published like a layer's output, in the posterior layer's chunk geometry
+        prev_nch = P.step[P.n_step - 1].NCH;
+        prev_nc = P.step[P.n_step - 1].NC;
+      }
       auto run = [&](const LayerDesc& ldref, const CUtensorMap* tm_w, int in_hi_buf, int in_lo_buf, int s, bool res_layer) {
         const int KB = ldref.KB, NCH = ldref.NCH, NC = ldref.NC, passes = ldref.passes;
         if (res_layer && !is_w) {
@@ -297,12 +337,21 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const uint8_t* w_img = ldref.w_img;
         const uint8_t* sc = scratch_of(tile_of(it, s), s);
         const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
-        const uint32_t par_shift = static_cast<uint32_t>(s) * MAX_ACT_CHUNKS;
+        const uint32_t bset = SPLIT ? (lk & 1u) : static_cast<uint32_t>(s);   // chunk-barrier set: sub-tile, or layer parity (split mode)
+        const uint32_t par_shift = bset * MAX_ACT_CHUNKS;
         int ready = 0;
+        auto wait_chunks = [&](int need) {
+          while (ready < need) {
+            mbar_wait(bar_act_chunk(bset, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
+            act_par ^= (1u << (par_shift + ready));
+            ++ready;
+            if (SPLIT) fence_acq_rel_cluster();   // the chunk was written by another CTA's TMA stores
+          }
+        };
         if (!is_w) SDRM_TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
         const int half_rows = NC >> 1;
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = c_first; c < NCH; c += c_step) {   // (split mode: this CTA's chunks; otherwise all)
           for (int p = 0; p < passes; ++p) {
             const int which = (p == 1) ? 1 : 0;
             const int a_buf = (p == 2) ? in_lo_buf : in_hi_buf;
@@ -314,14 +363,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             // activation half): twice the weight bytes in flight -- this mode is bound by the L2 latency of the weight stream
             const int kstep = res_layer ? 2 : 1;
             for (int kb = 0; kb < KB; kb += kstep) {
-              if (!is_w && c == 0 && p == 0) {
+              if (!is_w && c == c_first && p == 0) {
                 int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
                 if (need > prev_nch || kb == KB - 1) need = prev_nch;
-                while (ready < need) {
-                  mbar_wait(bar_act_chunk(s, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
-                  act_par ^= (1u << (par_shift + ready));
-                  ++ready;
-                }
+                wait_chunks(need);
                 if (kb == 0) SDRM_TR(0, 2);
               }
               mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
@@ -366,11 +411,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
           if (!is_w) SDRM_TR(0, 3);
         }
+        if (SPLIT && !is_w) wait_chunks(prev_nch);   // a CTA without a chunk in this layer still consumes the phases
       };
       // the layer whose output the NEXT layer of the same tile reads (all sub-tiles go through the same layer sequence)
       auto done = [&](const LayerDesc& ldref) {
         prev_nch = (ldref.kind == EPI_LINEAR_OUT) ? 0 : ldref.NCH;
         prev_nc = ldref.NC;
+        ++lk;
       };
       // chain layers ping-pong between activation buffers 0 and 1 (in = parity of the layer count so far); only two
       // hot buffers per tile keep the scratch L2-resident.  The decoder reads x0 hi from the chain's last buffer.
@@ -428,7 +475,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             tc_fence_after();
             SDRM_TR(1, 7);
           }
-          for (int c = 0; c < NCH; ++c) {
+          for (int c = c_first; c < NCH; c += c_step) {
             const uint32_t buf = cc & 1u;
             SDRM_TR(1, 1);
             mbar_wait(bar_acc_empty(buf), ((cc >> 1) & 1u) ^ 1u, err, WD_MMA_ACC);
@@ -517,6 +564,34 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // writes reach DRAM).  discard.global.L2 drops such lines without a write-back (tools/ubench_discard.cu: 15.4 GB -> 0.5 GB of
     // DRAM writes).  Only whole k-blocks that the next writer rewrites completely are discarded (discard_kb), so the zero
     // padding columns written once at kernel start survive.
+    if constexpr (SPLIT) {
+      // ===================================== relay warp (column-split mode) ======================================
+      // forwards "chunk c of the layer's output is complete in the L2" from this CTA's epilogue warps to the chunk barrier of
+      // every CTA of the cluster, lane j -> CTA j, with a cluster-scope release (this warp has no memory operation in flight)
+      uint32_t rk = 0;
+      auto forward = [&](uint32_t bset, int c) {
+        mbar_wait(bar_relay(rk), (rk >> 1) & 1u, err, WD_RELAY);
+        ++rk;
+        if (lane < static_cast<int>(split_n)) mbar_arrive_cluster_release(mapa_cluster(bar_act_chunk(bset, static_cast<uint32_t>(c)), static_cast<uint32_t>(lane)));
+        __syncwarp();
+      };
+      for (int it = 0; it < n_iters; ++it) {
+        if (tile_of(it, 0) >= n_tiles) break;
+        uint32_t lk = 0;
+        const LayerDesc& lo = P.step[P.n_step - 1];
+        for (int c = c_first; c < lo.NCH; c += c_step) forward(0u, c);   // x_T and the first input image
+        for (int i = P.T; i >= 1; --i)
+          for (int l = 0; l < P.n_step; ++l) {
+            ++lk;
+            for (int c = c_first; c < P.step[l].NCH; c += c_step) forward(lk & 1u, c);
+          }
+        for (int l = 0; l < P.n_dec; ++l) {
+          ++lk;
+          if (P.dec[l].kind != EPI_LINEAR_OUT && l != P.n_dec - 1)
+            for (int c = c_first; c < P.dec[l].NCH; c += c_step) forward(lk & 1u, c);
+        }
+      }
+    }
     if (PAIR && P.discard_kb > 0) {
       uint32_t dcnt = 0;   // layer counters of the sub-tiles
       const int n_lines = P.discard_kb * (A_TILE_BYTES / 128);
@@ -647,8 +722,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       }
     };
 
-    // zero the activation buffers once: K-padding columns must read as exact zeros
-    if (!P.preloaded_input) {
+    // zero the activation buffers once: K-padding columns must read as exact zeros (split mode: done by the whole cluster above)
+    if (!SPLIT && !P.preloaded_input) {
       for (int s = 0; s < NSUB; ++s) {
         uint4* z = reinterpret_cast<uint4*>(scratch_of(0, s));
         const size_t n16 = NUM_ACT_BUFS * P.act_buf_bytes / 16;
@@ -679,6 +754,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           }
         pub_pend = 0;
       }
+    };
+    uint32_t rk = 0;          // split mode: chunks handed to the relay warp so far (ring index / parity of bar_relay)
+    auto relay_chunk = [&]() {   // this warp's TMA stores of one own chunk have completed (stores_done() first)
+      if (lane0) mbar_arrive(bar_relay(rk));
+      ++rk;
     };
     uint32_t half_par = 0;    // parity of bar_half_read (resident mode, two-chunk layers)
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
@@ -728,7 +808,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           set_ctx(s);
           const unsigned long long grow = static_cast<unsigned long long>(P.row_offset + row);
           uint8_t* in0_row = sc + row_off;   // the first chain layer reads activation buffer 0
-          for (int g = sub; g < P.Lg16; g += EPI_SUB) {
+          // (split mode: only the columns of this CTA's chunks of the posterior layer -- the state columns it owns for the whole chain)
+          const int xg_per = SPLIT ? (P.step[P.n_step - 1].NC >> 4) : P.Lg16;
+          const int xg_blocks = SPLIT ? P.step[P.n_step - 1].NCH : 1;
+          for (int cb = c_first; cb < xg_blocks; cb += c_step)
+          for (int gg = sub; gg < xg_per; gg += EPI_SUB) {
+            const int g = cb * xg_per + gg;
+            if (g >= P.Lg16) break;
             float x[16];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -776,6 +862,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       fence_proxy_async();   // the zero fill of the buffers (generic stores) is read by the TMA loads too
       stores_done();
       if (lane == 0) mbar_arrive(bar_tile_ready);
+      if (SPLIT)
+        for (int c = c_first; c < P.step[P.n_step - 1].NCH; c += c_step) relay_chunk();   // the first input image: "layer 0" of the chunk-barrier ring
       if (RES && P.n_step > 0) res_publish();   // the first chain layer's input tile
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
@@ -817,12 +905,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         auto fetch_slice = [&](int c) -> float4 {
           return (lane < 4 * BIAS_SLOTS && slice_g < ngroups) ? *reinterpret_cast<const float4*>(bias_row + c * NC + slice_o) : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float4 bnext = fetch_slice(0);
+        float4 bnext = (c_first < NCH) ? fetch_slice(c_first) : make_float4(0.f, 0.f, 0.f, 0.f);
         // Resident layer: the output overwrites the layer's own input tile.  One chunk: its accumulator is complete, so every UMMA
         // has retired.  Two chunks: the first chunk's epilogue starts as soon as ITS accumulator is complete and only waits, before
         // its first store, until the second chunk's UMMAs have read the k-blocks under its columns (bar_half_read) -- it runs in
         // the shadow of the rest of the second chunk.
-        for (int c = 0; c < NCH; ++c) {
+        for (int c = c_first; c < NCH; c += c_step) {
           const uint32_t buf = cc & 1u;
           const uint32_t t_chunk = tmem_base + lane_addr + buf * 256u;
           const int fc = c * NC;
@@ -845,14 +933,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           };
           // does not depend on the accumulator: ask before waiting (first chunk only: later chunks fence first, and a membar
           // would wait for these loads to return)
-          if (KIND == EPI_POSTERIOR && c == 0 && sub < ngroups) request_state(sub);
+          if (KIND == EPI_POSTERIOR && c == c_first && sub < ngroups) request_state(sub);
           SDRM_TR_EPI(1);
           mbar_wait_sleepy(bar_acc_full(buf), (cc >> 1) & 1u, err, WD_EPI_ACC, 512);
           tc_fence_after();
           SDRM_TR_EPI(2);
           if (lazy) {
             publish_pending();
-          } else if (c > 0 && c == NCH - 2 && publishes) {
+          } else if (!SPLIT && c > 0 && c == NCH - 2 && publishes) {
             // Deferred publication of ALL earlier chunks (0 .. NCH-3) with ONE proxy fence: their stores were issued at least
             // a whole accumulator wait ago, and only the next layer reads these activations -- it cannot issue its first UMMA
             // before this layer's last chunk is in the tensor pipe.  (A fence.proxy.async is a membar.gpu round trip of ~1.3 us
@@ -864,8 +952,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               for (int cp = 0; cp < c; ++cp) mbar_arrive(bar_act_chunk(s, cp));
             SDRM_TR_EPI(5);
           }
-          if (c + 1 < NCH) bnext = fetch_slice(c + 1);   // after the fence: a membar would wait for this load to return
-          if (KIND == EPI_POSTERIOR && c > 0 && sub < ngroups) request_state(sub);
+          if (c + c_step < NCH) bnext = fetch_slice(c + c_step);   // after the fence: a membar would wait for this load to return
+          if (KIND == EPI_POSTERIOR && c != c_first && sub < ngroups) request_state(sub);
           if (res_layer && NCH == 2 && c == 0) {   // (before the TMEM load: with the accumulator registers live across a wait ptxas spills)
             mbar_wait(bar_half_read, half_par, err, WD_EPI_LAYER);
             half_par ^= 1u;
@@ -997,7 +1085,13 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           // publish the layer's LAST chunk to the TMA (async) proxy right away: the next layer's tail k-blocks wait for it
           // The last two chunks are published right away: the next layer's k-blocks wait for them.  For the second-to-last
           // chunk the fence sits in the slack before the last accumulator is ready; the last chunk's is the critical path.
-          if (publishes && lazy) {
+          if (SPLIT) {
+            if (publishes) {   // every own chunk right away, through the relay warp (cluster-wide chunk barriers)
+              stores_done();
+              relay_chunk();
+              SDRM_TR_EPI(5);
+            }
+          } else if (publishes && lazy) {
             pub_pend |= 1u << (8 * s + c);
           } else if (publishes && c >= NCH - 2) {
             stores_done();
@@ -1007,7 +1101,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         }
         if (KIND == EPI_POSTERIOR && last_step) {
           // x_0 pass: every thread re-reads the state columns it wrote itself (same chunk / group ownership as above)
-          for (int c = 0; c < NCH; ++c)
+          for (int c = c_first; c < NCH; c += c_step)
             for (int g = sub; g < ngroups; g += EPI_SUB) {
               const int g16 = ((c * NC) >> 4) + g;
               if (g16 >= P.Lg16) continue;
@@ -1029,7 +1123,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                   if (f0 + e < P.L) P.x0_out[static_cast<size_t>(row) * P.L + f0 + e] = x0v[e];
               }
             }
-          if (!last_of_tile && lazy) {
+          if (SPLIT) {
+            if (!last_of_tile) {
+              stores_done();
+              for (int c = c_first; c < NCH; c += c_step) relay_chunk();
+            }
+          } else if (!last_of_tile && lazy) {
             pub_pend |= ((1u << NCH) - 1u) << (8 * s);
           } else if (!last_of_tile) {
             stores_done();
@@ -1043,7 +1142,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           if (lane0) mbar_arrive(bar_state_ready(s));   // x_{i-1} is complete: the noise warps may prepare step i-1
         }
       };
-      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) {
+      auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) __attribute__((always_inline)) {
         set_ctx(s);
         switch (ld.kind) {
           case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
@@ -1114,7 +1213,35 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           st_par ^= 1u << s;
         }
         // ---- (1) keep masks of step i-1 (F.dropout p = .5 of the NEXT forward, train_SDRM.py:100)
-        if (i > 1) {
+        if (SPLIT && i > 1) {
+          // split mode: only the 16-bit pieces of this CTA's own column groups -- a peer may already be a layer ahead and must
+          // not have its bits of the same 128-column block overwritten with the next step's
+          const LayerDesc& lo = P.step[P.n_step - 1];
+          uint16_t* mask16 = reinterpret_cast<uint16_t*>(mask_row);
+          for (int c = c_first; c < lo.NCH; c += c_step) {
+            const int g_lo = c * (lo.NC >> 4), g_hi = min(g_lo + (lo.NC >> 4), Lg16);
+            for (int b = g_lo >> 3; b <= ((g_hi - 1) >> 3) && g_lo < g_hi; ++b) {
+              uint32_t ww[4] = {0, 0, 0, 0};
+              if (valid) {
+                if (P.inj_mask) {
+                  const uint8_t* mp = P.inj_mask + (static_cast<size_t>(i - 1) * P.n_rows + row) * L;
+                  for (int e = 0; e < 128; ++e) {
+                    const int f = b * 128 + e;
+                    if (f < L && mp[f]) ww[e >> 5] |= 1u << (e & 31);
+                  }
+                } else {
+                  const u32x4 m4 = philox_mask128(K, STREAM_MASK, grow, static_cast<uint32_t>(i - 1), static_cast<uint32_t>(b));
+                  ww[0] = m4.x; ww[1] = m4.y; ww[2] = m4.z; ww[3] = m4.w;
+                }
+              }
+              for (int g = max(g_lo, 8 * b); g < min(g_hi, 8 * b + 8); ++g) {
+                const int q8 = g & 7;
+                const uint32_t wsel = (q8 >> 1) == 0 ? ww[0] : (q8 >> 1) == 1 ? ww[1] : (q8 >> 1) == 2 ? ww[2] : ww[3];
+                mask16[g] = static_cast<uint16_t>((wsel >> (16 * (q8 & 1))) & 0xFFFFu);
+              }
+            }
+          }
+        } else if (i > 1) {
           const int nblk = (Lg16 + 7) >> 3;
           for (int b = 0; b < nblk; ++b) {
             uint4 w = make_uint4(0, 0, 0, 0);
@@ -1198,9 +1325,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             half_group(g16, 0, padded);
             half_group(g16, 1, padded);
           };
+          if (SPLIT) {   // the state columns this CTA owns (its chunks of the posterior layer)
+            const LayerDesc& lo = P.step[P.n_step - 1];
+            for (int c = c_first; c < lo.NCH; c += c_step) {
+              const int g_lo = c * (lo.NC >> 4), g_hi = min(g_lo + (lo.NC >> 4), Lg16);
 #pragma unroll 1
-          for (int g = 0; g < full_groups; ++g) group(g, false);
-          if (full_groups < Lg16) group(full_groups, true);
+              for (int g = g_lo; g < g_hi; ++g) group(g, g >= full_groups);
+            }
+          } else {
+#pragma unroll 1
+            for (int g = 0; g < full_groups; ++g) group(g, false);
+            if (full_groups < Lg16) group(full_groups, true);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_noise_ready(s));
@@ -1211,7 +1347,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its operands
+#undef c_first
+#undef c_step
+  if (PAIR || SPLIT) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its operands
   if (warp == M_WARP) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, 512);

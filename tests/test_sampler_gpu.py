@@ -150,6 +150,48 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
         assert torch.equal(a, o) and torch.equal(lat[0], l_)
 
 
+@pytest.mark.parametrize("shape", [
+    # n, I, H, L, T, nh      chain chunks -> cluster
+    (843, 1008, 930, 830, 9, 2),     # cfg-1 widths: 4 chunks of 208 -> 4 CTAs per tile, one chunk each (7 tiles = 28 CTAs)
+    (700, 400, 200, 520, 5, 1),      # 3 chunks of 176 on 4 CTAs (one idles in the chain); decoder layers of 1 and 2 chunks
+    (300, 2000, 1000, 950, 6, 4),    # cfg-5 widths, ragged last tile; 8 logits chunks -> two per CTA
+    (260, 600, 300, 1300, 4, 1),     # 6 chunks -> clusters of 8 (two idle CTAs)
+    (128, 300, 96, 600, 3, 0),       # a single row tile, no hidden layer
+])
+def test_column_split_mode_is_bit_identical_to_streaming(shape):
+    """Full-resolution launches of a few row tiles of a wide denoiser (>= 3 N chunks per chain layer) split every tile's chunks over
+    a cluster of 4 / 8 CTAs (engine_host.cu, SDRM_OPT_NO_SPLIT); the chunk barriers span the cluster.  Same arithmetic, same
+    rows, same latent as the one-CTA-per-tile flows, with in-kernel Philox noise and with injected noise tensors."""
+    from oracle import philox_ref
+    from sdrm_b200 import _lib
+    lib = _lib.load()
+    n, I, H, L, T, nh = shape
+    nch = -(-L // 256)
+    want = 4 if nch <= 4 else 8
+    diff, vae = random_modules(I, H, L, T, nh, seed=13, device="cuda")
+    eng = _engine(diff, vae, T, 1.0)
+    lat = [torch.empty(n, L, device="cuda") for _ in range(4)]
+    try:
+        a = eng.sample(n, seed=21, latent_out=lat[0], check=True).clone()
+        assert lib.sdrm_last_split_size(eng.handle) == want
+        a2 = eng.sample(n, seed=21, check=True).clone()          # (a second launch on the same scratch)
+        eng.set_option(_lib.OPT_NO_SPLIT, 1)
+        b = eng.sample(n, seed=21, latent_out=lat[1], check=True).clone()
+        assert lib.sdrm_last_split_size(eng.handle) == 0
+        inj = dict(zip(("inj_xT", "inj_z", "inj_keep"), (torch.from_numpy(t).cuda().contiguous() for t in philox_ref.sampler_noise(21, 0, n, L, T))))
+        d = eng.sample(n, seed=0, latent_out=lat[3], check=True, **inj).clone()
+        eng.set_option(_lib.OPT_NO_SPLIT, 0)
+        c = eng.sample(n, seed=0, latent_out=lat[2], check=True, **inj)
+        assert lib.sdrm_last_split_size(eng.handle) == want
+    finally:
+        eng.set_option(_lib.OPT_NO_SPLIT, 0)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, a2)
+    assert torch.equal(a, b) and torch.equal(lat[0], lat[1])
+    assert torch.equal(c, d) and torch.equal(lat[2], lat[3])
+    assert rel_fro(c.cpu(), a.cpu()) < 1e-4   # (the numpy restatement of the noise differs from MUFU Box-Muller in the last bits)
+
+
 def test_interleaved_sub_tiles_are_bit_identical():
     """A CTA pair that owns several row tiles interleaves two of them layer by layer (ChainParams::n_sub = 2, an odd last
     tile runs alone); the grid cap makes a small launch take that path (12 row tiles on 2 pairs = 3 tiles per CTA)."""

@@ -342,10 +342,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         int ready = 0;
         auto wait_chunks = [&](int need) {
           while (ready < need) {
-            mbar_wait(bar_act_chunk(bset, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
+            // (split mode: the chunk was written by another CTA's TMA stores and arrives with a cluster-scope release; the acquire
+            // sits on the wait itself -- a fence.acq_rel.cluster behind it cost 1.1 us per chunk, 4.4 us of an 11 us layer)
+            mbar_wait<SPLIT>(bar_act_chunk(bset, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
             act_par ^= (1u << (par_shift + ready));
             ++ready;
-            if (SPLIT) fence_acq_rel_cluster();   // the chunk was written by another CTA's TMA stores
           }
         };
         if (!is_w) SDRM_TR(0, 1);

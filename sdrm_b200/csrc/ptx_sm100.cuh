@@ -78,25 +78,39 @@ static __constant__ unsigned long long g_sdrm_watchdog_ns = SDRM_WATCHDOG_NS;
 #ifndef SDRM_WAIT_HINT_NS
 #define SDRM_WAIT_HINT_NS 200000u
 #endif
+// CL: acquire at CLUSTER scope (the phase was completed by another CTA's release.cluster arrival: column-split chunk barriers)
+template <bool CL = false>
 __device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(hint_ns)
-      : "memory");
+  if (CL)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
   return ok;
 }
 // bounded wait: the timer is only read every 256 expired hints
+template <bool CL = false>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_word, int code) {
-  if (mbar_try_wait_hint(bar, parity, SDRM_WAIT_HINT_NS)) return;
+  if (mbar_try_wait_hint<CL>(bar, parity, SDRM_WAIT_HINT_NS)) return;
   uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait_hint(bar, parity, SDRM_WAIT_HINT_NS)) {
+  while (!mbar_try_wait_hint<CL>(bar, parity, SDRM_WAIT_HINT_NS)) {
     if ((++spins & 0xffu) == 0) {
       const uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;

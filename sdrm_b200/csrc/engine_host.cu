@@ -38,6 +38,21 @@ static Geom make_geom(int N, int K) {
   return g;
 }
 
+// Column-split geometry (clusters of SPLIT_S CTAs per row tile, see the kernel): a layer of fewer than SPLIT_S chunks is re-cut
+// into SPLIT_S narrower ones, so that every CTA of the cluster owns one -- half the weight bytes and half the epilogue per SM
+// of the 4-chunk geometry (the L2 -> SM port, ~64 B/clk, bounds a split layer: A image + own weight slices).
+constexpr int SPLIT_S = 8;
+static Geom make_geom_split(int N, int K) {
+  Geom g = make_geom(N, K);
+  if (g.NCH >= SPLIT_S) return g;
+  g.NCH = SPLIT_S;
+  const int per = (N + g.NCH - 1) / g.NCH;
+  g.NC = std::max(16, ((per + 15) / 16) * 16);
+  g.Np = g.NCH * g.NC;
+  return g;
+}
+static bool same_geom(const Geom& a, const Geom& b) { return a.NCH == b.NCH && a.NC == b.NC && a.KB == b.KB; }
+
 // ------------------------------------------------------------------------------------------------
 // packing kernels
 // ------------------------------------------------------------------------------------------------
@@ -217,6 +232,11 @@ struct sdrm_handle {
   float nd = 1.0f;
   Geom g0, gh, go;
   uint8_t *w0 = nullptr, *wh = nullptr, *wo = nullptr;
+  // column-split geometry (8 chunks per layer) and its weight images; packed for denoisers wider than 512 (>= 3 normal chunks)
+  Geom s0, sh, so, s1, s2;
+  uint8_t *w0s = nullptr, *whs = nullptr, *wos = nullptr, *w1s = nullptr, *w2s = nullptr;
+  bool split_den = false, split_dec = false;
+  int np0 = 0, nph = 0, npo = 0, np1 = 0, np2 = 0;   // padded bias widths (both geometries fit)
   float *bias0 = nullptr, *bh = nullptr, *bo = nullptr, *slopes = nullptr, *coef = nullptr;
   // K6 (small denoisers, small_chain_kernel.cuh): zero-padded bf16 images and 64-wide bias rows, packed when every width <= 64
   bool small_den = false, small_dec = false;
@@ -236,6 +256,8 @@ struct sdrm_handle {
 
 static void free_den(sdrm_handle* h) {
   cudaFree(h->w0); cudaFree(h->wh); cudaFree(h->wo);
+  cudaFree(h->w0s); cudaFree(h->whs); cudaFree(h->wos);
+  h->w0s = h->whs = h->wos = nullptr; h->split_den = false;
   cudaFree(h->bias0); cudaFree(h->bh); cudaFree(h->bo); cudaFree(h->slopes); cudaFree(h->coef);
   cudaFree(h->s_den); cudaFree(h->s_bias);
   h->s_den = nullptr; h->s_bias = nullptr; h->small_den = false;
@@ -245,6 +267,8 @@ static void free_den(sdrm_handle* h) {
 }
 static void free_dec(sdrm_handle* h) {
   cudaFree(h->w1); cudaFree(h->w2); cudaFree(h->b1); cudaFree(h->b2);
+  cudaFree(h->w1s); cudaFree(h->w2s);
+  h->w1s = h->w2s = nullptr; h->split_dec = false;
   cudaFree(h->s_dec1); cudaFree(h->s_dec2); cudaFree(h->s_b1);
   h->s_dec1 = h->s_dec2 = nullptr; h->s_b1 = nullptr; h->small_dec = false;
   h->w1 = h->w2 = nullptr;
@@ -465,12 +489,24 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
     h->g0 = make_geom(D, L);
     h->gh = make_geom(D, D);
     h->go = make_geom(L, D);
+    h->s0 = make_geom_split(D, L);
+    h->sh = make_geom_split(D, D);
+    h->so = make_geom_split(L, D);
+    h->np0 = std::max(h->g0.Np, h->s0.Np); h->nph = std::max(h->gh.Np, h->sh.Np); h->npo = std::max(h->go.Np, h->so.Np);
     SDRM_CUDA(cudaMalloc(&h->w0, h->g0.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->wh, h->gh.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->wo, h->go.img_bytes()));
-    SDRM_CUDA(cudaMalloc(&h->bias0, sizeof(float) * (T + 1) * h->g0.Np));
-    SDRM_CUDA(cudaMalloc(&h->bh, sizeof(float) * h->gh.Np));
-    SDRM_CUDA(cudaMalloc(&h->bo, sizeof(float) * h->go.Np));
+    // a second set of images in the column-split geometry: wide denoisers only (>= 3 chunks per layer, where the split applies)
+    h->split_den = std::min(h->g0.NCH, h->go.NCH) >= 3 && (nh == 0 || h->gh.NCH >= 3) &&
+                   !(same_geom(h->g0, h->s0) && same_geom(h->gh, h->sh) && same_geom(h->go, h->so));
+    if (h->split_den) {
+      SDRM_CUDA(cudaMalloc(&h->w0s, h->s0.img_bytes()));
+      SDRM_CUDA(cudaMalloc(&h->whs, h->sh.img_bytes()));
+      SDRM_CUDA(cudaMalloc(&h->wos, h->so.img_bytes()));
+    }
+    SDRM_CUDA(cudaMalloc(&h->bias0, sizeof(float) * (T + 1) * h->np0));
+    SDRM_CUDA(cudaMalloc(&h->bh, sizeof(float) * h->nph));
+    SDRM_CUDA(cudaMalloc(&h->bo, sizeof(float) * h->npo));
     SDRM_CUDA(cudaMalloc(&h->slopes, sizeof(float) * 2));
     SDRM_CUDA(cudaMalloc(&h->coef, sizeof(float) * 4 * (T + 1)));
   }
@@ -478,9 +514,14 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
   launch_pack_weight(d_W0, D, L, L + T, 0, h->w0, nullptr, h->g0, st);
   if (nh > 0) launch_pack_weight(d_Wh, D, D, D, 0, h->wh, nullptr, h->gh, st);
   launch_pack_weight(d_Wo, L, D, D, 0, h->wo, nullptr, h->go, st);
-  bias_table_kernel<<<T + 1, 256, sizeof(float) * 2 * T, st>>>(d_We, d_be, d_W0, d_b0, T, L, D, h->bias0, h->g0.Np);
-  pad_bias_kernel<<<(h->gh.Np + 255) / 256, 256, 0, st>>>(nh > 0 ? d_bh : nullptr, D, h->bh, h->gh.Np);
-  pad_bias_kernel<<<(h->go.Np + 255) / 256, 256, 0, st>>>(d_bo, L, h->bo, h->go.Np);
+  if (h->split_den) {
+    launch_pack_weight(d_W0, D, L, L + T, 0, h->w0s, nullptr, h->s0, st);
+    if (nh > 0) launch_pack_weight(d_Wh, D, D, D, 0, h->whs, nullptr, h->sh, st);
+    launch_pack_weight(d_Wo, L, D, D, 0, h->wos, nullptr, h->so, st);
+  }
+  bias_table_kernel<<<T + 1, 256, sizeof(float) * 2 * T, st>>>(d_We, d_be, d_W0, d_b0, T, L, D, h->bias0, h->np0);
+  pad_bias_kernel<<<(h->nph + 255) / 256, 256, 0, st>>>(nh > 0 ? d_bh : nullptr, D, h->bh, h->nph);
+  pad_bias_kernel<<<(h->npo + 255) / 256, 256, 0, st>>>(d_bo, L, h->bo, h->npo);
   SDRM_CUDA(cudaMemcpyAsync(h->slopes, d_a0, sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (nh > 0) SDRM_CUDA(cudaMemcpyAsync(h->slopes + 1, d_ah, sizeof(float), cudaMemcpyDeviceToDevice, st));
   coef_kernel<<<(T + 1 + 127) / 128, 128, 0, st>>>(d_sched, T, noise_divider, h->coef);
@@ -494,7 +535,7 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
     pack_small_weight_kernel<<<18, 256, 0, st>>>(d_W0, D, L, L + T, 0, 64, h->s_den, nullptr);
     pack_small_weight_kernel<<<18, 256, 0, st>>>(nh > 0 ? d_Wh : d_Wo, nh > 0 ? D : 0, nh > 0 ? D : 0, D, 0, 64, h->s_den + img, nullptr);
     pack_small_weight_kernel<<<18, 256, 0, st>>>(d_Wo, L, D, D, 0, 64, h->s_den + 2 * img, nullptr);
-    pad_rows64_kernel<<<(64 * (T + 1) + 255) / 256, 256, 0, st>>>(h->bias0, h->g0.Np, D, T + 1, h->s_bias);
+    pad_rows64_kernel<<<(64 * (T + 1) + 255) / 256, 256, 0, st>>>(h->bias0, h->np0, D, T + 1, h->s_bias);
     pad_rows64_kernel<<<1, 64, 0, st>>>(nh > 0 ? d_bh : nullptr, 0, D, 1, h->s_bias + 64 * (T + 1));
     pad_rows64_kernel<<<1, 64, 0, st>>>(d_bo, 0, L, 1, h->s_bias + 64 * (T + 2));
     SDRM_CUDA(cudaGetLastError());
@@ -519,15 +560,25 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
     h->H = H; h->I = I;
     h->g1 = make_geom(H, L);
     h->g2 = make_geom(I, H);
+    h->s1 = make_geom_split(H, L);
+    h->s2 = make_geom_split(I, H);
+    h->np1 = std::max(h->g1.Np, h->s1.Np); h->np2 = std::max(h->g2.Np, h->s2.Np);
     SDRM_CUDA(cudaMalloc(&h->w1, 2 * h->g1.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->w2, 2 * h->g2.img_bytes()));
-    SDRM_CUDA(cudaMalloc(&h->b1, sizeof(float) * h->g1.Np));
-    SDRM_CUDA(cudaMalloc(&h->b2, sizeof(float) * h->g2.Np));
+    h->split_dec = L > 2 * MAX_NC;   // the denoiser this decoder follows may take the column split (it is at least L wide)
+    if (h->split_dec) {
+      if (!same_geom(h->g1, h->s1)) SDRM_CUDA(cudaMalloc(&h->w1s, 2 * h->s1.img_bytes()));
+      if (!same_geom(h->g2, h->s2)) SDRM_CUDA(cudaMalloc(&h->w2s, 2 * h->s2.img_bytes()));
+    }
+    SDRM_CUDA(cudaMalloc(&h->b1, sizeof(float) * h->np1));
+    SDRM_CUDA(cudaMalloc(&h->b2, sizeof(float) * h->np2));
   }
   launch_pack_weight(d_W1, H, L, L, 0, h->w1, h->w1 + h->g1.img_bytes(), h->g1, st);
   launch_pack_weight(d_W2, I, H, H, 0, h->w2, h->w2 + h->g2.img_bytes(), h->g2, st);
-  pad_bias_kernel<<<(h->g1.Np + 255) / 256, 256, 0, st>>>(d_b1, H, h->b1, h->g1.Np);
-  pad_bias_kernel<<<(h->g2.Np + 255) / 256, 256, 0, st>>>(d_b2, I, h->b2, h->g2.Np);
+  if (h->w1s) launch_pack_weight(d_W1, H, L, L, 0, h->w1s, h->w1s + h->s1.img_bytes(), h->s1, st);
+  if (h->w2s) launch_pack_weight(d_W2, I, H, H, 0, h->w2s, h->w2s + h->s2.img_bytes(), h->s2, st);
+  pad_bias_kernel<<<(h->np1 + 255) / 256, 256, 0, st>>>(d_b1, H, h->b1, h->np1);
+  pad_bias_kernel<<<(h->np2 + 255) / 256, 256, 0, st>>>(d_b2, I, h->b2, h->np2);
   SDRM_CUDA(cudaGetLastError());
   if (L <= SMALL_MAX && H <= SMALL_MAX) {   // K6 images
     const size_t img = static_cast<size_t>(64) * SMALL_KP;
@@ -554,9 +605,11 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
 static int kb_max_of(const sdrm_handle* h) {
   int kb = 1;
   const Geom* gs[5] = {&h->g0, &h->gh, &h->go, &h->g1, &h->g2};
+  const Geom* ss[4] = {&h->s0, &h->sh, &h->so, &h->s1};
   for (int i = 0; i < 4; ++i) {  // g2 writes logits, not activations
     kb = std::max(kb, gs[i]->KB);
     kb = std::max(kb, (gs[i]->Np + KBLK - 1) / KBLK);
+    if (h->split_den && h->split_dec) kb = std::max(kb, (ss[i]->Np + KBLK - 1) / KBLK);   // (the column-split geometry pads wider)
   }
   kb = std::max(kb, h->g2.KB);
   return kb;
@@ -652,13 +705,39 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   };
   // chain layers ping-pong between activation buffers 0/1 (the kernel derives the parity); decoder descriptors name
   // their hi buffers RELATIVE to the chain's last output (0 = that buffer, 1 = the other), lo buffers are 2 and 3
+  // Column-split mode (see the kernel): full-resolution chains of a FEW row tiles of a WIDE denoiser (>= 3 N chunks per chain
+  // layer, i.e. wider than the resident flow takes): a cluster of S CTAs per tile, CTA j computes the chunks c = j (mod S).  One
+  // tile per cluster, all clusters resident at once.  Preferred: S = 8 in the 8-chunk geometry (second set of weight images);
+  // else S = 4 in the normal geometry (3 - 4 chunks).
+  const long long n_tiles = (n + TILE_M - 1) / TILE_M;
+  int split = 0;
+  bool split_geom = false;
+  {
+    int nch_min = std::min(h->g0.NCH, h->go.NCH), nch_max = std::max(h->g0.NCH, h->go.NCH);
+    if (h->nh > 0) { nch_min = std::min(nch_min, h->gh.NCH); nch_max = std::max(nch_max, h->gh.NCH); }
+    const int ov = h->cluster_override;
+    auto fits = [&](int S) {
+      return h->split_resident[S] > 0 && n_tiles * S <= h->split_resident[S] && (h->grid_limit == 0 || n_tiles * S <= h->grid_limit);
+    };
+    if (d_t_start == nullptr && !h->no_split && nch_min >= 3 && (ov == 0 || ov >= 4)) {
+      const bool geom8 = h->split_den && h->split_dec;
+      if ((ov == 0 || ov == 8) && fits(8) && (geom8 || nch_max > 4)) { split = 8; split_geom = geom8; }
+      else if ((ov == 4 || (ov == 0 && nch_max <= 4)) && fits(4)) split = 4;
+    }
+  }
+  h->last_split = split;
+  const Geom& G0 = split_geom ? h->s0 : h->g0;
+  const Geom& GH = split_geom ? h->sh : h->gh;
+  const Geom& GO = split_geom ? h->so : h->go;
+  const Geom& G1 = split_geom ? h->s1 : h->g1;
+  const Geom& G2 = split_geom ? h->s2 : h->g2;
   int l = 0;
-  fill(P.step[l++], h->w0, h->bias0, h->slopes, h->g0.Np, h->g0, 1, EPI_PRELU, 0, 0, 0, 0);
-  for (int j = 0; j < h->nh; ++j) fill(P.step[l++], h->wh, h->bh, h->slopes + 1, 0, h->gh, 1, EPI_PRELU, 0, 0, 0, 0);
-  fill(P.step[l++], h->wo, h->bo, nullptr, 0, h->go, 1, EPI_POSTERIOR, 0, 0, 0, 0);
+  fill(P.step[l++], split_geom ? h->w0s : h->w0, h->bias0, h->slopes, h->np0, G0, 1, EPI_PRELU, 0, 0, 0, 0);
+  for (int j = 0; j < h->nh; ++j) fill(P.step[l++], split_geom ? h->whs : h->wh, h->bh, h->slopes + 1, 0, GH, 1, EPI_PRELU, 0, 0, 0, 0);
+  fill(P.step[l++], split_geom ? h->wos : h->wo, h->bo, nullptr, 0, GO, 1, EPI_POSTERIOR, 0, 0, 0, 0);
   P.n_step = l;
-  fill(P.dec[0], h->w1, h->b1, nullptr, 0, h->g1, 3, EPI_TANH_SPLIT, 0, 2, 1, 3);
-  fill(P.dec[1], h->w2, h->b2, nullptr, 0, h->g2, 3, EPI_LINEAR_OUT, 1, 3, 0, 0);
+  fill(P.dec[0], (split_geom && h->w1s) ? h->w1s : h->w1, h->b1, nullptr, 0, G1, 3, EPI_TANH_SPLIT, 0, 2, 1, 3);
+  fill(P.dec[1], (split_geom && h->w2s) ? h->w2s : h->w2, h->b2, nullptr, 0, G2, 3, EPI_LINEAR_OUT, 1, 3, 0, 0);
   P.n_dec = 2;
   P.T = h->T; P.L = h->L; P.Lg16 = (h->L + 15) / 16;
   P.preloaded_input = 0;
@@ -678,26 +757,11 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   P.err_word = h->err_word;
   P.trace = h->trace;
   P.debug_flags = h->debug_flags;
-  const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int cluster = 1;
   // full-resolution chains run on tcgen05 cta_group::2 CTA pairs (fewer weight bytes and more k-blocks in flight per SM);
   // multi-resolution chains (per-tile step counts) and single-tile calls use single-CTA mode
   if (d_t_start == nullptr && n_tiles >= 2) cluster = 2;
   if (h->cluster_override > 0 && (d_t_start == nullptr || h->cluster_override == 1)) cluster = h->cluster_override;
-  // Column-split mode (see the kernel): full-resolution chains of a FEW row tiles of a WIDE denoiser (3 - 8 N chunks per chain
-  // layer, i.e. wider than the resident flow takes): a cluster of S = 4 / 8 CTAs per tile, CTA j computes the chunks c = j (mod S).
-  // One tile per cluster, all clusters resident at once.
-  int split = 0;
-  {
-    int nch_min = MAX_ACT_CHUNKS, nch_max = 0;
-    for (int j = 0; j < P.n_step; ++j) { nch_min = std::min(nch_min, P.step[j].NCH); nch_max = std::max(nch_max, P.step[j].NCH); }
-    if (d_t_start == nullptr && P.n_step > 0 && !h->no_split && nch_min >= 3 && (h->cluster_override == 0 || h->cluster_override >= 4)) {
-      int S = nch_max <= 4 ? 4 : 8;
-      if (h->cluster_override >= 4) S = h->cluster_override;
-      if (h->split_resident[S] > 0 && n_tiles * S <= h->split_resident[S] && (h->grid_limit == 0 || n_tiles * S <= h->grid_limit)) split = S;
-    }
-  }
-  h->last_split = split;
   int launch_grid = 0;
   if (split) { cluster = 1; launch_grid = static_cast<int>(n_tiles) * split; }
   else

@@ -151,23 +151,23 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
 
 
 @pytest.mark.parametrize("shape", [
-    # n, I, H, L, T, nh      chain chunks -> cluster
-    (843, 1008, 930, 830, 9, 2),     # cfg-1 widths: 4 chunks of 208 -> 4 CTAs per tile, one chunk each (7 tiles = 28 CTAs)
-    (700, 400, 200, 520, 5, 1),      # 3 chunks of 176 on 4 CTAs (one idles in the chain); decoder layers of 1 and 2 chunks
-    (300, 2000, 1000, 950, 6, 4),    # cfg-5 widths, ragged last tile; 8 logits chunks -> two per CTA
-    (260, 600, 300, 1300, 4, 1),     # 6 chunks -> clusters of 8 (two idle CTAs)
+    # n, I, H, L, T, nh      normal geometry -> 8-chunk geometry (clusters of 8); clusters of 4 keep the normal geometry
+    (843, 1008, 930, 830, 9, 2),     # cfg-1 widths: 4 chunks of 208 -> 8 of 112 (7 tiles = 56 CTAs)
+    (700, 400, 200, 520, 5, 1),      # 3 chunks of 176 (on 4 CTAs one idles in the chain) -> 8 of 80; decoder layers of 1 and 2 chunks
+    (300, 2000, 1000, 950, 6, 4),    # cfg-5 widths, ragged last tile; 8 logits chunks in either geometry (two per CTA on 4 CTAs)
+    (260, 600, 300, 1300, 4, 1),     # 6 chunks of 224 -> 8 of 176 (on 4 CTAs: two chunks for CTAs 0 and 1)
     (128, 300, 96, 600, 3, 0),       # a single row tile, no hidden layer
 ])
 def test_column_split_mode_is_bit_identical_to_streaming(shape):
     """Full-resolution launches of a few row tiles of a wide denoiser (>= 3 N chunks per chain layer) split every tile's chunks over
-    a cluster of 4 / 8 CTAs (engine_host.cu, SDRM_OPT_NO_SPLIT); the chunk barriers span the cluster.  Same arithmetic, same
-    rows, same latent as the one-CTA-per-tile flows, with in-kernel Philox noise and with injected noise tensors."""
+    a cluster of 8 CTAs in an 8-chunk geometry of the layers (a second set of weight images), or of 4 CTAs in the normal geometry
+    (engine_host.cu, SDRM_OPT_NO_SPLIT / SDRM_OPT_CLUSTER); the chunk barriers span the cluster.  Same arithmetic, same rows, same
+    latent as the one-CTA-per-tile flows, with in-kernel Philox noise and with injected noise tensors."""
     from oracle import philox_ref
     from sdrm_b200 import _lib
     lib = _lib.load()
     n, I, H, L, T, nh = shape
-    nch = -(-L // 256)
-    want = 4 if nch <= 4 else 8
+    want = 8
     diff, vae = random_modules(I, H, L, T, nh, seed=13, device="cuda")
     eng = _engine(diff, vae, T, 1.0)
     lat = [torch.empty(n, L, device="cuda") for _ in range(4)]
@@ -175,6 +175,10 @@ def test_column_split_mode_is_bit_identical_to_streaming(shape):
         a = eng.sample(n, seed=21, latent_out=lat[0], check=True).clone()
         assert lib.sdrm_last_split_size(eng.handle) == want
         a2 = eng.sample(n, seed=21, check=True).clone()          # (a second launch on the same scratch)
+        eng.set_option(_lib.OPT_CLUSTER, 4)
+        a4 = eng.sample(n, seed=21, check=True).clone()
+        assert lib.sdrm_last_split_size(eng.handle) == 4
+        eng.set_option(_lib.OPT_CLUSTER, 0)
         eng.set_option(_lib.OPT_NO_SPLIT, 1)
         b = eng.sample(n, seed=21, latent_out=lat[1], check=True).clone()
         assert lib.sdrm_last_split_size(eng.handle) == 0
@@ -185,8 +189,9 @@ def test_column_split_mode_is_bit_identical_to_streaming(shape):
         assert lib.sdrm_last_split_size(eng.handle) == want
     finally:
         eng.set_option(_lib.OPT_NO_SPLIT, 0)
+        eng.set_option(_lib.OPT_CLUSTER, 0)
     assert torch.isfinite(a).all()
-    assert torch.equal(a, a2)
+    assert torch.equal(a, a2) and torch.equal(a, a4)
     assert torch.equal(a, b) and torch.equal(lat[0], lat[1])
     assert torch.equal(c, d) and torch.equal(lat[2], lat[3])
     assert rel_fro(c.cpu(), a.cpu()) < 1e-4   # (the numpy restatement of the noise differs from MUFU Box-Muller in the last bits)

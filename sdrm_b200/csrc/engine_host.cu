@@ -827,6 +827,13 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     }
   }
   h->last_resident = P.resident;
+  if (split) {
+    int nc_max = 16;
+    for (int j = 0; j < P.n_step; ++j) nc_max = std::max(nc_max, P.step[j].NC);
+    for (int j = 0; j < P.n_dec; ++j) nc_max = std::max(nc_max, P.dec[j].NC);
+    P.split_stage_bytes = static_cast<uint32_t>(A_TILE_BYTES + (nc_max * 128 + 1023) / 1024 * 1024);
+    P.res_nstg = std::max(1, std::min(6, static_cast<int>(4u * STAGE_BYTES / P.split_stage_bytes)));
+  }
   if (static_cast<size_t>(split ? n_tiles : launch_grid) * P.n_sub * stride > workspace_bytes)
     return sdrm_fail(SDRM_ERR_WORKSPACE, "sdrm_sample: workspace too small for the sub-tile scratch slots");
   rc = launch_engine(P, launch_grid, cluster, st, split);

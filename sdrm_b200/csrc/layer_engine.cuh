@@ -97,6 +97,8 @@ struct ChainParams {
   int discard_kb;         // pair mode: k-blocks of a chain layer's dead input image the discard warp drops from the L2 (0 = off)
   int resident;           // pair mode, one row tile per CTA: the chain's activation tile lives in shared memory (see the kernel)
   int res_nstg;           // resident mode: pipeline stages left to the weight / decoder stream (the rest of the ring holds the tile)
+                          // column-split mode: stages of split_stage_bytes in the 192 KB ring (4 .. 6)
+  uint32_t split_stage_bytes;   // column-split mode: A_TILE_BYTES + the widest chunk's weight k-block, 1024-byte multiple
   int* err_word;
   // pair mode only: TMA tensor maps over the weight blobs (rows of 128 B, box = NC/2 rows) and over the whole
   // activation scratch (box = 128 rows); tensor-map loads may complete on the LEADER CTA's mbarrier (.cta_group::2)

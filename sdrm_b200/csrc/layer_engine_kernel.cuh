@@ -43,6 +43,11 @@
 #define SDRM_OUT_SLOTS 1      // shared-memory boxes per epilogue warp for the TMA activation stores; 2 = the store of a box is issued one group later
                               // (measured r02: 278.7 / 277.4 vs 275.1 / 273.7 ms per cfg-5 shard on one box: the epilogue is not the critical path there)
 #endif
+#ifndef SDRM_SPLIT_RELAY
+#define SDRM_SPLIT_RELAY 0    // column-split mode: 1 = chunk publications go through the relay warp with a cluster-scope release (see the kernel);
+                              // 0 = the epilogue warps arrive on the peers' chunk barriers themselves (default: 2.70 -> 2.54 ms at cfg 1 for dropping
+                              // the release alone)
+#endif
 #ifndef SDRM_STATE_CS
 #define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
 #endif
@@ -58,6 +63,8 @@
 #define SDRM_DEBUG_NOISE_NO_STATE (P.debug_flags & 32)     // Philox / Box-Muller without the state load / store
 #define SDRM_DEBUG_ACT_STORE_FIXED (P.debug_flags & 64)    // every activation box goes to row 0 of the CTA's scratch (no new dirty lines)
 #define SDRM_DEBUG_NO_STORE_WAIT (P.debug_flags & 128)     // publish chunks without waiting for the TMA stores to complete
+#define SDRM_DEBUG_SKIP_A_LOADS (P.debug_flags & 256)      // single-CTA / split mode: no activation loads (the stage's arrival only)
+#define SDRM_DEBUG_SKIP_W_LOADS (P.debug_flags & 512)      // single-CTA / split mode: no weight loads
 #else
 #define SDRM_DEBUG_SKIP_ACT_STORES 0
 #define SDRM_DEBUG_SKIP_NOISE 0
@@ -65,6 +72,8 @@
 #define SDRM_DEBUG_NOISE_NO_STATE 0
 #define SDRM_DEBUG_ACT_STORE_FIXED 0
 #define SDRM_DEBUG_NO_STORE_WAIT 0
+#define SDRM_DEBUG_SKIP_A_LOADS 0
+#define SDRM_DEBUG_SKIP_W_LOADS 0
 #endif
 
 namespace sdrm {
@@ -139,10 +148,16 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // barrier map (8 bytes each): full[NSTG] | empty[NSTG] | (unused NSTG) | acc_full[2] | acc_empty[2] | tile_ready |
   //                             act_chunk[MAX_SUB][MAX_ACT_CHUNKS] | state_ready[MAX_SUB] | noise_ready[MAX_SUB] |
   //                             layer_consumed[MAX_SUB][2] | discard_done[MAX_SUB][2]
-  auto stage_a = [&](uint32_t s) { return base_addr + s * STG_BYTES; };
-  auto stage_w = [&](uint32_t s) { return base_addr + s * STG_BYTES + A_TILE_BYTES; };
+  // column-split mode: the stage size follows the launch's widest chunk (A 16 KB + NC x 128 B of weights), so that up to 6 stages
+  // fit the same 192 KB ring -- a split layer is bound by the hops of the ring (commit -> empty -> producer -> full -> issuer),
+  // not by bytes: measured with the loads switched off it ran only 7 % faster
+  constexpr int NSTG_B = SPLITK ? 6 : NSTG;   // barrier slots per array (2 x 6 fit the 3 x 4 slots of the single-CTA map)
+  static_assert(2 * NSTG_B <= 3 * NSTG, "full / empty barrier slots");
+  const uint32_t stg_bytes = SPLITK ? P.split_stage_bytes : STG_BYTES;
+  auto stage_a = [&](uint32_t s) { return base_addr + s * stg_bytes; };
+  auto stage_w = [&](uint32_t s) { return base_addr + s * stg_bytes + A_TILE_BYTES; };
   auto bar_full = [&](uint32_t s) { return bar_base + 8u * s; };
-  auto bar_empty = [&](uint32_t s) { return bar_base + 8u * (NSTG + s); };
+  auto bar_empty = [&](uint32_t s) { return bar_base + 8u * (NSTG_B + s); };
   auto bar_acc_full = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + b); };
   auto bar_acc_empty = [&](uint32_t b) { return bar_base + 8u * (3 * NSTG + 2 + b); };
   const uint32_t bar_tile_ready = bar_base + 8u * (3 * NSTG + 4);
@@ -202,7 +217,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 #define c_step (SPLIT ? static_cast<int>(cluster_nctarank()) : 1)
 
   if (warp == W_WARP && lane == 0) {
-    for (int s = 0; s < NSTG; ++s) {
+    for (int s = 0; s < NSTG_B; ++s) {
       mbar_init(bar_full(s), 2);     // weight producer + activation producer each arm their own byte count
       mbar_init(bar_empty(s), 1);    // one tcgen05.commit per consumed stage
     }
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_acc_empty(0), EPI_WARPS * (PAIR ? 2 : 1));   // the leader's UMMA issuer waits for the epilogue warps of both CTAs
     mbar_init(bar_acc_empty(1), EPI_WARPS * (PAIR ? 2 : 1));
     for (int s = 0; s < MAX_SUB; ++s) {
-      for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), SPLIT ? 1 : EPI_WARPS);   // (split: one relayed arrival)
+      for (int c = 0; c < MAX_ACT_CHUNKS; ++c) mbar_init(bar_act_chunk(s, c), (SPLIT && SDRM_SPLIT_RELAY) ? 1 : EPI_WARPS);   // (relayed split publications: one arrival)
       mbar_init(bar_state_ready(s), EPI_WARPS);
       mbar_init(bar_noise_ready(s), NOISE_WARPS);
       for (uint32_t k = 0; k < 2; ++k) {
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // (the peer CTA's half of the M = 256 operand is signalled through its idle UMMA warp with a cluster-scope release).  The
   // weights still stream from the L2; x_0 goes to the scratch as bf16 hi / lo and the decoder runs as in streaming mode.
   constexpr bool RES = RESK;
-  const uint32_t nstg = RES ? static_cast<uint32_t>(P.res_nstg) : static_cast<uint32_t>(NSTG);
+  const uint32_t nstg = (RES || SPLIT) ? static_cast<uint32_t>(P.res_nstg) : static_cast<uint32_t>(NSTG);   // (split: stages of split_stage_bytes)
   const uint32_t res_a = base_addr + nstg * STG_BYTES;
 
   const long long n_tiles = (P.n_rows + TILE_M - 1) / TILE_M;
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   int* err = P.err_word;
 #ifdef SDRM_TRACE
   int trace_n = 0;
-  const bool tracing = (P.trace != nullptr) && (blockIdx.x == 0) && (lane == 0 || warp < W_WARP);
+  const bool tracing = (P.trace != nullptr) && (blockIdx.x == static_cast<unsigned>(P.debug_flags >> 16)) && (lane == 0 || warp < W_WARP);   // (traced CTA: bits 16+ of the debug flags)
   unsigned long long trace_seq = 0;  // k-block sequence number of the role (for matching producer / consumer events)
   const bool trace_kb = (P.debug_flags & 8) != 0;   // per-k-block events perturb the pipeline; off by default
   auto TR = [&](int role, unsigned long long code) {
@@ -342,11 +357,18 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         int ready = 0;
         auto wait_chunks = [&](int need) {
           while (ready < need) {
-            // (split mode: the chunk was written by another CTA's TMA stores and arrives with a cluster-scope release; the acquire
-            // sits on the wait itself -- a fence.acq_rel.cluster behind it cost 1.1 us per chunk, 4.4 us of an 11 us layer)
+            // (split mode: the chunk was written by another CTA's TMA stores, whose completion that CTA has observed (bulk wait_group)
+            // before its relay warp arrived here: the bytes are in the L2, and the only reader is this warp's TMA load, which reads
+            // the L2 directly -- no cache of this SM is involved.  A cluster-scope acquire costs ~1 us per wait, as a fence behind the
+            // wait (fence.acq_rel.cluster) and as a qualifier on it (try_wait.acquire.cluster) alike: 8 of them were 60 % of a layer.)
+#ifdef SDRM_SPLIT_ACQUIRE_CLUSTER
             mbar_wait<SPLIT>(bar_act_chunk(bset, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
+#else
+            mbar_wait(bar_act_chunk(bset, ready), (act_par >> (par_shift + ready)) & 1u, err, WD_PRODUCER_ACT);
+#endif
             act_par ^= (1u << (par_shift + ready));
             ++ready;
+            if (SPLIT) SDRM_TR(0, 6);
           }
         };
         if (!is_w) SDRM_TR(0, 1);
@@ -367,6 +389,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               if (!is_w && c == c_first && p == 0) {
                 int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
                 if (need > prev_nch || kb == KB - 1) need = prev_nch;
+#ifdef SDRM_PERF_DEBUG
+                if (P.debug_flags & 1024) need = prev_nch;   // (experiment: wait for the whole input image before the first k-block)
+#endif
                 wait_chunks(need);
                 if (kb == 0) SDRM_TR(0, 2);
               }
@@ -394,11 +419,17 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     tma_load_2d_pair_hint(mapa_cluster(stage_a(stage), cta_rank), &P.tm_act, 0, a_row, fb0, pol_keep);
                   }
                 } else if (is_w) {
-                  mbar_arrive_expect_tx(fb, w_bytes);
-                  bulk_g2s_hint(stage_w(stage), w_src, w_bytes, fb, pol_keep);
+                  if (SDRM_DEBUG_SKIP_W_LOADS) mbar_arrive(fb);
+                  else {
+                    mbar_arrive_expect_tx(fb, w_bytes);
+                    bulk_g2s_hint(stage_w(stage), w_src, w_bytes, fb, pol_keep);
+                  }
                 } else {
-                  mbar_arrive_expect_tx(fb, A_TILE_BYTES);
-                  tma_load_2d_hint(stage_a(stage), &P.tm_act, 0, a_row, fb, pol_keep);
+                  if (SDRM_DEBUG_SKIP_A_LOADS) mbar_arrive(fb);
+                  else {
+                    mbar_arrive_expect_tx(fb, A_TILE_BYTES);
+                    tma_load_2d_hint(stage_a(stage), &P.tm_act, 0, a_row, fb, pol_keep);
+                  }
                 }
               }
               __syncwarp();
@@ -565,8 +596,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // writes reach DRAM).  discard.global.L2 drops such lines without a write-back (tools/ubench_discard.cu: 15.4 GB -> 0.5 GB of
     // DRAM writes).  Only whole k-blocks that the next writer rewrites completely are discarded (discard_kb), so the zero
     // padding columns written once at kernel start survive.
-    if constexpr (SPLIT) {
-      // ===================================== relay warp (column-split mode) ======================================
+    if constexpr (SPLIT && SDRM_SPLIT_RELAY) {
+      // ===================================== relay warp (column-split mode, -DSDRM_SPLIT_RELAY=1) ================
       // forwards "chunk c of the layer's output is complete in the L2" from this CTA's epilogue warps to the chunk barrier of
       // every CTA of the cluster, lane j -> CTA j, with a cluster-scope release (this warp has no memory operation in flight)
       uint32_t rk = 0;
@@ -756,10 +787,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         pub_pend = 0;
       }
     };
-    uint32_t rk = 0;          // split mode: chunks handed to the relay warp so far (ring index / parity of bar_relay)
-    auto relay_chunk = [&]() {   // this warp's TMA stores of one own chunk have completed (stores_done() first)
-      if (lane0) mbar_arrive(bar_relay(rk));
-      ++rk;
+    // Split mode: publish own chunk c of the layer's output to every CTA of the cluster.  This warp's TMA stores of the chunk have
+    // completed (stores_done() first: lane 0 has waited for its bulk group, the __syncwarp behind it orders the other lanes), i.e. the
+    // bytes are in the L2, and the only readers are the peers' TMA loads, which read the L2 directly -- so lane j arrives on CTA j's
+    // chunk barrier with the default (CTA-scope) release, like every cross-CTA "slot is free" signal of a TMA pipeline.  The
+    // cluster-scope release (through the relay warp, -DSDRM_SPLIT_RELAY=1) costs 0.5 us per layer and changes no result.
+    uint32_t rk = 0;          // relay build: chunks handed to the relay warp so far; default: layers of this tile so far (chunk-barrier set)
+    auto relay_chunk = [&](int c) {
+      if (SDRM_SPLIT_RELAY) {
+        if (lane0) mbar_arrive(bar_relay(rk));
+        ++rk;
+      } else {
+        if (lane < static_cast<int>(cluster_nctarank()))
+          mbar_arrive_cluster(mapa_cluster(bar_act_chunk(rk & 1u, static_cast<uint32_t>(c)), static_cast<uint32_t>(lane)));
+      }
     };
     uint32_t half_par = 0;    // parity of bar_half_read (resident mode, two-chunk layers)
     uint32_t noise_par = 0;   // bit s: parity of sub-tile s's noise_ready barrier
@@ -774,6 +815,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     for (; it < n_iters; ++it) {
       if (!PAIR && tile_of(it, 0) >= n_tiles) break;
       const int ns = nsub_of(it);
+      if (SPLIT && !SDRM_SPLIT_RELAY) rk = 0;   // (the producers' layer count restarts with every tile)
       auto set_ctx = [&](int s) {
         sc = scratch_of(tile_of(it, s), s);
         xs = reinterpret_cast<float*>(sc + NUM_ACT_BUFS * P.act_buf_bytes);
@@ -864,7 +906,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       stores_done();
       if (lane == 0) mbar_arrive(bar_tile_ready);
       if (SPLIT)
-        for (int c = c_first; c < P.step[P.n_step - 1].NCH; c += c_step) relay_chunk();   // the first input image: "layer 0" of the chunk-barrier ring
+        for (int c = c_first; c < P.step[P.n_step - 1].NCH; c += c_step) relay_chunk(c);   // the first input image: "layer 0" of the chunk-barrier ring
       if (RES && P.n_step > 0) res_publish();   // the first chain layer's input tile
 
       // ---- layers: one instantiation per epilogue kind so that the group loop carries no dispatch
@@ -1089,7 +1131,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           if (SPLIT) {
             if (publishes) {   // every own chunk right away, through the relay warp (cluster-wide chunk barriers)
               stores_done();
-              relay_chunk();
+              relay_chunk(c);
               SDRM_TR_EPI(5);
             }
           } else if (publishes && lazy) {
@@ -1127,7 +1169,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           if (SPLIT) {
             if (!last_of_tile) {
               stores_done();
-              for (int c = c_first; c < NCH; c += c_step) relay_chunk();
+              for (int c = c_first; c < NCH; c += c_step) relay_chunk(c);
             }
           } else if (!last_of_tile && lazy) {
             pub_pend |= ((1u << NCH) - 1u) << (8 * s);
@@ -1145,6 +1187,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       };
       auto run_kind = [&](const LayerDesc& ld, int step, bool last_of_tile, int out_hi_buf, int out_lo_buf, int s) __attribute__((always_inline)) {
         set_ctx(s);
+        if (SPLIT && !SDRM_SPLIT_RELAY) ++rk;   // this layer's output goes to chunk-barrier set rk & 1
         switch (ld.kind) {
           case EPI_PRELU: run(std::integral_constant<int, EPI_PRELU>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;
           case EPI_POSTERIOR: run(std::integral_constant<int, EPI_POSTERIOR>{}, ld, step, last_of_tile, out_hi_buf, out_lo_buf, s); break;

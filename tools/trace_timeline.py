@@ -21,7 +21,7 @@ eng.set_option(_lib.OPT_TRACE_BUFFER, buf.data_ptr())
 out = sample_ddpm(rows, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=2)
 torch.cuda.synchronize(); eng.set_option(_lib.OPT_TRACE_BUFFER, 0)
 ev = buf.cpu().numpy().astype("uint64").reshape(3, CAP)
-names = {0: {1: "P.layer_begin", 2: "P.act_ready", 3: "P.chunk_issued", 4: "P.empty_ok", 5: "P.issued"}, 1: {1: "M.chunk_begin", 2: "M.acc_free", 3: "M.first_full", 4: "M.chunk_committed", 5: "M.full_ok", 6: "M.kb_issued", 7: "M.a_ready"},
+names = {0: {1: "P.layer_begin", 2: "P.act_ready", 3: "P.chunk_issued", 4: "P.empty_ok", 5: "P.issued", 6: "P.chunk_ok"}, 1: {1: "M.chunk_begin", 2: "M.acc_free", 3: "M.first_full", 4: "M.chunk_committed", 5: "M.full_ok", 6: "M.kb_issued", 7: "M.a_ready"},
          2: {1: "E.wait", 2: "E.acc_full", 3: "E.chunk_done", 4: "E.noise_done", 5: "E.layer_done"}}
 allv = []
 for role in range(3):

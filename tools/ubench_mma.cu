@@ -6,7 +6,7 @@
 #include "../sdrm_b200/csrc/ptx_sm100.cuh"
 using namespace sdrm;
 
-__global__ void __launch_bounds__(128, 1) mma_kernel(int N, int iters, int stages, const uint8_t* src, int tma_bytes, int tma_iters, int commit_each) {
+__global__ void __launch_bounds__(128, 1) mma_kernel(int N, int iters, int stages, const uint8_t* src, int tma_bytes, int tma_iters, int commit_each, int alt = 0) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + 4 * 49152;
@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int N, int iters, int stage
     for (int i = 0; i < iters; ++i) {
       const uint32_t st = (stages > 1) ? (i % stages) : 0;
       const uint64_t a = umma_desc_sw128(base + st * 49152), b = umma_desc_sw128(base + st * 49152 + 16384);
-      const uint32_t d = tmem + ((i / 15) & 1) * 256;
+      const uint32_t d = alt ? tmem + (i & 1) * 256 : tmem + ((i / 15) & 1) * 256;   // alt: consecutive k-blocks accumulate into different TMEM columns
       for (int k = 0; k < 4; ++k) umma_bf16_ss(d, a + 2u * k, b + 2u * k, idesc, (i % 15) | k);
       if (commit_each) umma_commit(bars + 16);
       if (commit_each == 2) { tc_fence_after(); }
@@ -49,17 +49,18 @@ int main() {
   uint8_t* src; cudaMalloc(&src, 1 << 20); cudaMemset(src, 0, 1 << 20);
   cudaFuncSetAttribute(mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 49152 + 2048);
   const int iters = 20000;
-  for (int tma = 0; tma < 2; ++tma)
-    for (int stages = 1; stages <= 3; stages += 2)
-      for (int N : {64, 128, 240, 256}) {
+  for (int alt = 0; alt < 2; ++alt)
+  for (int tma = 1; tma < 2; ++tma)
+    for (int stages = 3; stages <= 3; stages += 2)
+      for (int N : {64, 112, 128, 208, 256}) {
         cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-        mma_kernel<<<sms, 128, 4 * 49152 + 2048>>>(N, 100, stages, src, 49152, 0, tma);
+        mma_kernel<<<sms, 128, 4 * 49152 + 2048>>>(N, 100, stages, src, 49152, 0, tma, alt);
         cudaEventRecord(e0);
-        mma_kernel<<<sms, 128, 4 * 49152 + 2048>>>(N, iters, stages, src, 49152, 0, tma);
+        mma_kernel<<<sms, 128, 4 * 49152 + 2048>>>(N, iters, stages, src, 49152, 0, tma, alt);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         const double flops = 2.0 * 128 * N * 64 * (double)iters * sms;
-        printf("commit_each=%d stages=%d N=%3d: %7.3f ms  %7.1f ns per 64-K block  %7.1f TFLOP/s  (%s)\n", tma, stages, N, ms, ms * 1e6 / iters,
+        printf("alt=%d commit_each=%d stages=%d N=%3d: %7.3f ms  %7.1f ns per 64-K block  %7.1f TFLOP/s  (%s)\n", alt, tma, stages, N, ms, ms * 1e6 / iters,
                flops / ms / 1e9, cudaGetErrorString(cudaGetLastError()));
       }
   return 0;

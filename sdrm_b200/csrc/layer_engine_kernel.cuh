@@ -318,6 +318,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     // the compiler wrap every uniform-datapath instruction (UBLKCP / UTMALDG / UTCHMMA) in an elect loop and costs
     // ~0.5 us per k-block.  The weight stream does not depend on the previous layer's epilogue and runs ahead.
     const bool is_w = (warp == W_WARP);
+#ifdef SDRM_TRACE
+    const bool tr_me = is_w == ((P.debug_flags & 4096) != 0);   // the traced producer: activations, or (flag 4096) weights
+#else
+    constexpr bool tr_me = false;
+#endif
     const uint64_t pol_keep = l2_policy_evict_last();
     uint32_t stage = 0, sphase = 0, act_par = 0;   // act_par: one parity bit per chunk-index barrier (sub-tile s: bits 8s..8s+7)
     static_assert(MAX_SUB * MAX_ACT_CHUNKS <= 32, "act_par bits");
@@ -354,9 +359,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int a_row_base = static_cast<int>((static_cast<size_t>(sc - P.scratch)) >> 7);
         const uint32_t bset = SPLIT ? (lk & 1u) : static_cast<uint32_t>(s);   // chunk-barrier set: sub-tile, or layer parity (split mode)
         const uint32_t par_shift = bset * MAX_ACT_CHUNKS;
-        int ready = 0;
-        auto wait_chunks = [&](int need) {
-          while (ready < need) {
+        // The k-block loop of this warp is a serial instruction chain that a split layer's tensor work (0.24 us per k-block) does
+        // not hide: no division, no special-register reads in it (the chunk need is tracked as covered features; measured with
+        // loads AND UMMAs switched off the loop ran at 0.4 us per k-block with an integer division and an S2R per iteration).
+        int ready = 0, covered = 0;   // chunks of the input image waited for so far, and the features they cover
+        bool gate = !is_w;            // the first (chunk, pass) this warp streams waits for the input image chunk by chunk
+        auto wait_chunks = [&](int lim) {
+          while (ready < prev_nch && covered < lim) {
+            covered += prev_nc;
             // (split mode: the chunk was written by another CTA's TMA stores, whose completion that CTA has observed (bulk wait_group)
             // before its relay warp arrived here: the bytes are in the L2, and the only reader is this warp's TMA load, which reads
             // the L2 directly -- no cache of this SM is involved.  A cluster-scope acquire costs ~1 us per wait, as a fence behind the
@@ -371,7 +381,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             if (SPLIT) SDRM_TR(0, 6);
           }
         };
-        if (!is_w) SDRM_TR(0, 1);
+        if (tr_me) SDRM_TR(0, 1);
         const uint32_t w_bytes = static_cast<uint32_t>(NC) * 128u;          // one whole weight k-block image
         const int half_rows = NC >> 1;
         for (int c = c_first; c < NCH; c += c_step) {   // (split mode: this CTA's chunks; otherwise all)
@@ -386,13 +396,12 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             // activation half): twice the weight bytes in flight -- this mode is bound by the L2 latency of the weight stream
             const int kstep = res_layer ? 2 : 1;
             for (int kb = 0; kb < KB; kb += kstep) {
-              if (!is_w && c == c_first && p == 0) {
-                int need = ((kb + 1) * KBLK + prev_nc - 1) / prev_nc;
-                if (need > prev_nch || kb == KB - 1) need = prev_nch;
+              if (gate) {
+                int lim = (kb == KB - 1) ? 0x7fffffff : (kb + 1) * KBLK;   // k-block kb needs the chunks covering features < 64 (kb + 1)
 #ifdef SDRM_PERF_DEBUG
-                if (P.debug_flags & 1024) need = prev_nch;   // (experiment: wait for the whole input image before the first k-block)
+                if (P.debug_flags & 1024) lim = 0x7fffffff;   // (experiment: wait for the whole input image before the first k-block)
 #endif
-                wait_chunks(need);
+                wait_chunks(lim);
                 if (kb == 0) SDRM_TR(0, 2);
               }
               mbar_wait(bar_empty(stage), sphase ^ 1, err, WD_PRODUCER_EMPTY);
@@ -437,13 +446,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
               a_row += A_TILE_BYTES >> 7;
               w_src += w_bytes;
               a_src += A_TILE_BYTES;
-              if (!is_w) { SDRM_TR(0, 5); SDRM_TR_SEQ(); }
+              if (tr_me) { SDRM_TR(0, 5); SDRM_TR_SEQ(); }
               if (++stage == nstg) { stage = 0; sphase ^= 1; }
             }
+            gate = false;
           }
-          if (!is_w) SDRM_TR(0, 3);
+          if (tr_me) SDRM_TR(0, 3);
         }
-        if (SPLIT && !is_w) wait_chunks(prev_nch);   // a CTA without a chunk in this layer still consumes the phases
+        if (SPLIT && !is_w) wait_chunks(0x7fffffff);   // a CTA without a chunk in this layer still consumes the phases
       };
       // the layer whose output the NEXT layer of the same tile reads (all sub-tiles go through the same layer sequence)
       auto done = [&](const LayerDesc& ldref) {
@@ -551,10 +561,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
                     if (nk > 3) umma_bf16_ss_pair(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
                     umma_commit_pair(bar_empty(stage), static_cast<uint16_t>((1u << CS) - 1u));   // every CTA of the cluster
                   } else {
+#ifdef SDRM_PERF_DEBUG
+                    if (!(P.debug_flags & 2048))   // (experiment: no UMMAs, only the commits -- the pace of the barrier machinery alone)
+#endif
+                    {
                     umma_bf16_ss(d_tmem, a_desc, b_desc, idesc, acc);
                     if (nk > 1) umma_bf16_ss(d_tmem, a_desc + 2u, b_desc + 2u, idesc, 1u);
                     if (nk > 2) umma_bf16_ss(d_tmem, a_desc + 4u, b_desc + 4u, idesc, 1u);
                     if (nk > 3) umma_bf16_ss(d_tmem, a_desc + 6u, b_desc + 6u, idesc, 1u);
+                    }
                     umma_commit(bar_empty(stage));
                   }
                 }

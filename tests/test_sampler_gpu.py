@@ -129,6 +129,7 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
     diff, vae = random_modules(I, H, L, T, nh, seed=11, device="cuda")
     eng = _engine(diff, vae, T, 1.0)
     lat = [torch.empty(n, L, device="cuda") for _ in range(4)]
+    eng.set_option(_lib.OPT_NO_SPLIT, 1)    # (launches of a few row tiles would take the column-split flow: its own test below)
     try:
         a = eng.sample(n, seed=5, latent_out=lat[0], check=True).clone()
         assert lib.sdrm_last_resident_mode(eng.handle) == (1 if fits and w > 128 else 0)
@@ -146,6 +147,7 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
         eng.set_option(_lib.OPT_RESIDENT, 0)
         eng.set_option(_lib.OPT_GRID_LIMIT, 0)
         eng.set_option(_lib.OPT_SUBTILES, 0)
+        eng.set_option(_lib.OPT_NO_SPLIT, 0)
     for o, l_ in ((b, lat[1]), (c, lat[2]), (d, lat[3])):
         assert torch.equal(a, o) and torch.equal(lat[0], l_)
 
@@ -157,6 +159,8 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
     (300, 2000, 1000, 950, 6, 4),    # cfg-5 widths, ragged last tile; 8 logits chunks in either geometry (two per CTA on 4 CTAs)
     (260, 600, 300, 1300, 4, 1),     # 6 chunks of 224 -> 8 of 176 (on 4 CTAs: two chunks for CTAs 0 and 1)
     (128, 300, 96, 600, 3, 0),       # a single row tile, no hidden layer
+    (1208, 729, 550, 400, 8, 0),     # cfg-4 widths: 2 chunks of 208 -> 8 of 64 (the resident flow's territory: the split is faster)
+    (900, 500, 300, 264, 6, 2),      # 2 chunks of 144 -> 8 of 48
 ])
 def test_column_split_mode_is_bit_identical_to_streaming(shape):
     """Full-resolution launches of a few row tiles of a wide denoiser (>= 3 N chunks per chain layer) split every tile's chunks over

@@ -474,6 +474,23 @@ def secondary_kernels(args, w, dev, diff, vae, out, peaks):
     ms = best_ms(lambda: be.noise_inputs(mu, t, ab_t, w["nd"], 0.1, 11, 0))
     gbs = 5.0 * 4.0 * B * w["L"] / (ms * 1e-3) / 1e9
     res["noise_inputs"] = {"ms": ms, "GBps": gbs, "frac_of_hbm_peak": gbs / peaks["hbm"], "rows": B, "L": w["L"]}
+    # BASELINE.json configs 1-4 (dataset-sized calls, the latency regime): one sample_ddpm of all N_USERS rows at the full T
+    from sdrm_b200 import _lib
+    from sdrm_b200.train_SDRM import engine_for
+    lib = _lib.load()
+    ds = {}
+    for name in ("cfg1", "cfg2", "cfg3", "cfg4"):
+        wd = WORKLOADS[name]
+        d2, v2 = build_models(wd, dev)
+        o2 = torch.empty(wd["n"], wd["I"], device=dev)
+        ms = best_ms(lambda: sample_ddpm(wd["n"], d2, v2, wd["L"], wd["nd"], n_timesteps=wd["T"], seed=3, out=o2, reuse_packed=True), reps=5)
+        hdl = engine_for(d2, dev).handle
+        split, resident, cluster = lib.sdrm_last_split_size(hdl), lib.sdrm_last_resident_mode(hdl), lib.sdrm_last_cluster_size(hdl)
+        flow = (f"column split, clusters of {split}" if split else "small-chain kernel (K6)" if cluster == 0 else
+                "resident tile" if resident else "streaming pairs" if cluster == 2 else "single CTAs")
+        ds[name] = {"ms": ms, "users_per_s": wd["n"] / (ms * 1e-3), "rows": wd["n"], "items": wd["I"], "T": wd["T"], "flow": flow}
+        del d2, v2, o2
+    res["dataset_configs"] = ds
     return res
 
 

@@ -708,7 +708,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // Column-split mode (see the kernel): full-resolution chains of a FEW row tiles of a WIDE denoiser (>= 3 N chunks per chain
   // layer, i.e. wider than the resident flow takes): a cluster of S CTAs per tile, CTA j computes the chunks c = j (mod S).  One
   // tile per cluster, all clusters resident at once.  Preferred: S = 8 in the 8-chunk geometry (second set of weight images);
-  // else S = 4 in the normal geometry (3 - 4 chunks).
+  // else S = 2 / 4 in the normal geometry (2 / 3 - 4 chunks).
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int split = 0;
   bool split_geom = false;
@@ -719,7 +719,8 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
     auto fits = [&](int S) {
       return h->split_resident[S] > 0 && n_tiles * S <= h->split_resident[S] && (h->grid_limit == 0 || n_tiles * S <= h->grid_limit);
     };
-    if (d_t_start == nullptr && !h->no_split && nch_min >= 2 && (ov == 0 || ov >= 4)) {
+    // (multi-resolution chains too: the tile's start step is the maximum over its rows in every CTA of the cluster alike)
+    if (!h->no_split && nch_min >= 2 && (ov == 0 || ov >= 4)) {
       const bool geom8 = h->split_den && h->split_dec;
       const int s_norm = nch_max <= 2 ? 2 : nch_max <= 4 ? 4 : 8;   // cluster size that gives every chunk of the normal geometry its CTA
       if ((ov == 0 || ov == 8) && fits(8) && (geom8 || nch_max > 4)) { split = 8; split_geom = geom8; }

@@ -183,8 +183,13 @@ def test_column_split_mode_is_bit_identical_to_streaming(shape):
         a4 = eng.sample(n, seed=21, check=True).clone()
         assert lib.sdrm_last_split_size(eng.handle) == 4
         eng.set_option(_lib.OPT_CLUSTER, 0)
+        ts = torch.from_numpy(np.random.RandomState(3).randint(1, T, size=n).astype(np.int32)).cuda()
+        e = eng.sample(n, t_start=ts, seed=21, check=True).clone()      # multi-resolution chains (per-row start steps) split too
+        assert lib.sdrm_last_split_size(eng.handle) == want
         eng.set_option(_lib.OPT_NO_SPLIT, 1)
         b = eng.sample(n, seed=21, latent_out=lat[1], check=True).clone()
+        assert lib.sdrm_last_split_size(eng.handle) == 0
+        f = eng.sample(n, t_start=ts, seed=21, check=True).clone()      # multi-resolution chains, one CTA per tile
         assert lib.sdrm_last_split_size(eng.handle) == 0
         inj = dict(zip(("inj_xT", "inj_z", "inj_keep"), (torch.from_numpy(t).cuda().contiguous() for t in philox_ref.sampler_noise(21, 0, n, L, T))))
         d = eng.sample(n, seed=0, latent_out=lat[3], check=True, **inj).clone()
@@ -198,6 +203,7 @@ def test_column_split_mode_is_bit_identical_to_streaming(shape):
     assert torch.equal(a, a2) and torch.equal(a, a4)
     assert torch.equal(a, b) and torch.equal(lat[0], lat[1])
     assert torch.equal(c, d) and torch.equal(lat[2], lat[3])
+    assert torch.equal(e, f)
     assert rel_fro(c.cpu(), a.cpu()) < 1e-4   # (the numpy restatement of the noise differs from MUFU Box-Muller in the last bits)
 
 

@@ -642,7 +642,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the side measurements (random mode, K3, K4, K2) of the default run")
     ap.add_argument("--no-eager", action="store_true", help="--impl reference: skip the eager-CUDA run of the reference")
     ap.add_argument("--eager-rows", type=int, default=None, help="--impl reference: rows of the eager-CUDA sample")
-    ap.add_argument("--cluster", type=int, default=0, help="force single CTAs (1) or tcgen05 CTA pairs (2); 0 = auto")
+    ap.add_argument("--cluster", type=int, default=0, help="force single CTAs (1), tcgen05 CTA pairs (2) or column-split clusters (4, 8); 0 = auto")
     ap.add_argument("--subtiles", type=int, default=0, help="row tiles a CTA pair interleaves (1, 2); 0 = auto")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

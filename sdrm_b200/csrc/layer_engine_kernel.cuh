@@ -202,12 +202,15 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   // idle, and the resident flow does not fit (tile > shared memory, N > 512 TMEM columns).  Here a cluster of S = 2 / 4 / 8 CTAs owns
   // ONE row tile: CTA j computes the N chunks c = j (mod S) of every layer over the full K -- it streams the whole activation image
   // and only its own chunks' weights -- and owns the same columns of the fp32 state, the keep bits and the noise.  Activations
-  // still travel through the tile's scratch in the L2 (TMA store -> TMA load), but the chunk barriers now span the cluster: a
-  // CTA's epilogue warps arrive on a local relay barrier once their TMA stores have completed, and the otherwise idle fourth
-  // control warp forwards ONE cluster-scope release arrival per chunk to the chunk barrier of every CTA of the cluster (an
-  // epilogue thread's own cluster-scope release would first drain its outstanding fp32 state stores).  The chunk barriers are a
-  // ring of two per chunk index (layer parity): a CTA can finish layer l + 1 before a slow peer has consumed layer l's
-  // phases, but not layer l + 2 (that needs the peer's chunk of layer l + 1).  One tile per cluster, full-resolution chains only.
+  // still travel through the tile's scratch in the L2 (TMA store -> TMA load), but the chunk barriers now span the cluster: once
+  // a warp's TMA stores of a chunk have completed, its lanes 0 .. S-1 arrive on the S peers' copies of the chunk barrier (see
+  // relay_chunk; -DSDRM_SPLIT_RELAY=1: through a local barrier and the otherwise idle fourth control warp, which forwards ONE
+  // cluster-scope release arrival per chunk -- an epilogue thread's own cluster-scope release would first drain its outstanding
+  // fp32 state stores).  The chunk barriers are a ring of two per chunk index (layer parity): a CTA can finish layer l + 1 before a
+  // slow peer has consumed layer l's phases, but not layer l + 2 (that needs the peer's chunk of layer l + 1).  The host launches
+  // ONE tile per cluster (a second tile's x_T pass would overwrite buffers a slower peer is still decoding from); full- and
+  // multi-resolution chains (every CTA of the cluster derives the same start step from the tile's rows).  The last layer of a
+  // tile must publish nothing (the decoder's logits layer: sdrm_sample always ends with it).
   constexpr bool SPLIT = SPLITK;
   const uint32_t split_n = SPLIT ? cluster_nctarank() : 1u;
   const uint32_t split_rank = SPLIT ? cluster_ctarank() : 0u;

@@ -725,7 +725,11 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
       const int s_norm = nch_max <= 2 ? 2 : nch_max <= 4 ? 4 : 8;   // cluster size that gives every chunk of the normal geometry its CTA
       if ((ov == 0 || ov == 8) && fits(8) && (geom8 || nch_max > 4)) { split = 8; split_geom = geom8; }
       else if (ov == 4 && fits(4)) split = 4;
-      else if (ov == 0 && s_norm < 8 && fits(s_norm)) split = s_norm;
+      else if (ov == 0) {
+        // more tiles than clusters of that size fit: smaller clusters, each CTA takes several chunks of a layer (c = j, j + S, ...)
+        for (int S = std::min(s_norm, 4); S >= 2 && !split; S >>= 1)
+          if (fits(S)) split = S;
+      }
     }
   }
   h->last_split = split;

@@ -496,8 +496,8 @@ int sdrm_denoiser_pack(sdrm_handle* h, const float* d_We, const float* d_be, con
     SDRM_CUDA(cudaMalloc(&h->w0, h->g0.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->wh, h->gh.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->wo, h->go.img_bytes()));
-    // a second set of images in the column-split geometry: wide denoisers only (>= 3 chunks per layer, where the split applies)
-    h->split_den = std::min(h->g0.NCH, h->go.NCH) >= 2 && (nh == 0 || h->gh.NCH >= 2) &&
+    // a second set of images in the column-split geometry (every layer re-cut into 8 chunks), unless it is the normal one
+    h->split_den = std::max(L, D) > SMALL_MAX &&   // (narrower denoisers run on the small-chain kernel)
                    !(same_geom(h->g0, h->s0) && same_geom(h->gh, h->sh) && same_geom(h->go, h->so));
     if (h->split_den) {
       SDRM_CUDA(cudaMalloc(&h->w0s, h->s0.img_bytes()));
@@ -565,7 +565,7 @@ int sdrm_decoder_pack(sdrm_handle* h, const float* d_W1, const float* d_b1, cons
     h->np1 = std::max(h->g1.Np, h->s1.Np); h->np2 = std::max(h->g2.Np, h->s2.Np);
     SDRM_CUDA(cudaMalloc(&h->w1, 2 * h->g1.img_bytes()));
     SDRM_CUDA(cudaMalloc(&h->w2, 2 * h->g2.img_bytes()));
-    h->split_dec = L > MAX_NC;   // the denoiser this decoder follows may take the column split (it is at least L wide)
+    h->split_dec = L > SMALL_MAX;   // the denoiser this decoder follows may take the column split
     if (h->split_dec) {
       if (!same_geom(h->g1, h->s1)) SDRM_CUDA(cudaMalloc(&h->w1s, 2 * h->s1.img_bytes()));
       if (!same_geom(h->g2, h->s2)) SDRM_CUDA(cudaMalloc(&h->w2s, 2 * h->s2.img_bytes()));
@@ -720,12 +720,12 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
       return h->split_resident[S] > 0 && n_tiles * S <= h->split_resident[S] && (h->grid_limit == 0 || n_tiles * S <= h->grid_limit);
     };
     // (multi-resolution chains too: the tile's start step is the maximum over its rows in every CTA of the cluster alike)
-    if (!h->no_split && nch_min >= 2 && (ov == 0 || ov >= 4)) {
+    if (!h->no_split && (ov == 0 || ov >= 4) && std::max(h->L, h->D) > SMALL_MAX) {
       const bool geom8 = h->split_den && h->split_dec;
       const int s_norm = nch_max <= 2 ? 2 : nch_max <= 4 ? 4 : 8;   // cluster size that gives every chunk of the normal geometry its CTA
       if ((ov == 0 || ov == 8) && fits(8) && (geom8 || nch_max > 4)) { split = 8; split_geom = geom8; }
       else if (ov == 4 && fits(4)) split = 4;
-      else if (ov == 0) {
+      else if (ov == 0 && nch_min >= 2) {
         // more tiles than clusters of that size fit: smaller clusters, each CTA takes several chunks of a layer (c = j, j + S, ...)
         for (int S = std::min(s_norm, 4); S >= 2 && !split; S >>= 1)
           if (fits(S)) split = S;

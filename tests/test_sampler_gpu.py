@@ -162,6 +162,8 @@ def test_resident_mode_is_bit_identical_to_streaming(shape):
     (1208, 729, 550, 400, 8, 0),     # cfg-4 widths: 2 chunks of 208 -> 8 of 64 (the resident flow's territory: the split is faster)
     (900, 500, 300, 264, 6, 2),      # 2 chunks of 144 -> 8 of 48
     (6000, 300, 200, 600, 3, 1),     # 47 row tiles: only clusters of 2 fit (normal geometry, CTA j takes the chunks j and j + 2 of 3)
+    (1500, 400, 128, 200, 7, 3),     # a single-chunk denoiser: 8 chunks of 32 columns
+    (500, 300, 100, 72, 9, 1),       # 8 chunks of 16 columns (the narrowest UMMA)
 ])
 def test_column_split_mode_is_bit_identical_to_streaming(shape):
     """Full-resolution launches of a few row tiles of a wide denoiser (>= 3 N chunks per chain layer) split every tile's chunks over

@@ -7,7 +7,7 @@ from helpers import random_modules
 from sdrm_b200 import _lib
 from sdrm_b200.engine import SamplerEngine
 from sdrm_b200.models import make_schedule
-for (L, H, I, T, nh, n) in [(830, 930, 1008, 83, 2, 2560), (830, 930, 1008, 83, 2, 4200), (830, 930, 1008, 83, 2, 9000), (950, 1000, 20000, 178, 4, 9000), (340, 490, 3125, 78, 1, 9000)]:
+for (L, H, I, T, nh, n) in [(200, 256, 3000, 60, 3, 1800), (128, 128, 2000, 50, 2, 1800), (96, 128, 1000, 40, 1, 1000), (830, 930, 1008, 83, 2, 2560), (830, 930, 1008, 83, 2, 4200), (830, 930, 1008, 83, 2, 9000), (950, 1000, 20000, 178, 4, 9000), (340, 490, 3125, 78, 1, 9000)]:
     diff, vae = random_modules(I, H, L, T, nh, seed=3, device="cuda")
     eng = SamplerEngine(); eng.pack_denoiser(diff, make_schedule(T, device="cuda"), 1.0); eng.pack_decoder(vae)
     out = torch.empty((n, I), dtype=torch.float32, device="cuda")

@@ -445,11 +445,11 @@ def secondary_kernels(args, w, dev, diff, vae, out, peaks):
 
     res = {}
     n, I = out.shape
-    # multi-resolution mode: row j runs t_j ~ U{1..T-1} steps (single-CTA tiles, rows sorted by chain length)
+    # multi-resolution mode: row j runs t_j ~ U{1..T-1} steps (rows sorted by chain length; CTA pairs since the third r02 session)
     n_r = min(n, 148 * 128)
     np.random.seed(0)
     ms = best_ms(lambda: sample_ddpm(n_r, diff, vae, w["L"], w["nd"], timesteps="random", n_timesteps=w["T"], seed=5, out=out[:n_r], reuse_packed=True))
-    res["sample_ddpm_random"] = {"users_per_s": n_r / (ms * 1e-3), "ms": ms, "rows": n_r, "note": "timesteps='random': mean chain length T/2, one 128-row tile per CTA"}
+    res["sample_ddpm_random"] = {"users_per_s": n_r / (ms * 1e-3), "ms": ms, "rows": n_r, "note": "timesteps='random': mean chain length T/2; CTA pairs, a pair runs the longer of its two tiles' chains"}
     # refill `out` with full-resolution logits for the score consumers below
     sample_ddpm(n, diff, vae, w["L"], w["nd"], n_timesteps=w["T"], seed=6, out=out, reuse_packed=True)
     # (the chain kernel leaves the board at its power cap with the SM clock near 1.2 GHz; the HBM-bound kernels below are timed

@@ -767,8 +767,9 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   int cluster = 1;
   // full-resolution chains run on tcgen05 cta_group::2 CTA pairs (fewer weight bytes and more k-blocks in flight per SM);
   // multi-resolution chains (per-tile step counts) and single-tile calls use single-CTA mode
-  if (d_t_start == nullptr && n_tiles >= 2) cluster = 2;
-  if (h->cluster_override > 0 && (d_t_start == nullptr || h->cluster_override == 1)) cluster = h->cluster_override;
+  // (multi-resolution chains too since the third r02 session: a pair runs the longer of its two tiles' chains)
+  if (n_tiles >= 2) cluster = 2;
+  if (h->cluster_override == 1 || h->cluster_override == 2) cluster = h->cluster_override;
   int launch_grid = 0;
   if (split) { cluster = 1; launch_grid = static_cast<int>(n_tiles) * split; }
   else
@@ -801,14 +802,14 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   int w_max = 0;
   for (int j = 0; j < P.n_step; ++j) w_max = std::max(w_max, std::max(P.step[j].KB * KBLK, P.step[j].NCH * P.step[j].NC));
   P.n_sub = 1;
-  if (cluster == 2 && n_local >= 2 && P.n_step > 0 &&
+  if (cluster == 2 && n_local >= 2 && P.n_step > 0 && d_t_start == nullptr &&   // (multi-resolution pairs: one tile at a time)
       (h->subtile_override == 2 || (h->subtile_override == 0 && w_max <= 320)))
     P.n_sub = 2;
   // Dead-buffer discard (pair mode, see the kernel's discard warp): whole k-blocks of a chain layer's input image that EVERY
   // chain layer's epilogue rewrites completely (64-column blocks below the narrowest written width), so a partly written
   // last k-block keeps the zero padding it got at kernel start.
   P.discard_kb = 0;
-  if (cluster >= 2 && !h->no_discard && h->T >= 2) {
+  if (cluster >= 2 && !h->no_discard && h->T >= 2 && d_t_start == nullptr) {   // (the discard warp counts P.T steps per tile)
     const int written = std::min(std::min(h->g0.Np, h->nh > 0 ? h->gh.Np : h->g0.Np), std::min(h->go.Np, P.Lg16 * 16));
     const int kb_read = std::min(std::min(h->g0.KB, h->nh > 0 ? h->gh.KB : h->g0.KB), h->go.KB);
     P.discard_kb = std::max(0, std::min(written / KBLK, kb_read));
@@ -819,7 +820,7 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   // (~9 TB/s of activation re-reads, weights, stores and state at 148 CTAs), and the resident tile removes the activation half of it
   // (cfg-2 widths, 100 000 users: 14.91 -> 14.39 ms; cfg-4 widths, 60 000 users: 5.55 -> 5.26 ms).
   P.resident = 0; P.res_nstg = 0;
-  if (cluster == 2 && P.n_sub == 1 && P.n_step > 0 && h->no_resident != 1 && (n_local >= 2 || w_max > 128)) {
+  if (cluster == 2 && P.n_sub == 1 && P.n_step > 0 && h->no_resident != 1 && d_t_start == nullptr && (n_local >= 2 || w_max > 128)) {
     int kb_max = 0;
     bool ok = true;
     for (int j = 0; j < P.n_step; ++j) {

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   constexpr int NCTA = CS;
   constexpr int BIAS_SLOTS = (16 + EPI_SUB - 1) / EPI_SUB;            // column groups of one chunk a warp can own
   constexpr uint32_t BIAS_SLICE_BYTES = BIAS_SLOTS * 16 * 4;         // per epilogue warp: the bias of its column groups of one chunk
-  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 5;   // mbarriers of a CTA (map below)
+  constexpr int NBAR = 3 * NSTG + 5 + MAX_SUB * (MAX_ACT_CHUNKS + 6) + 6;   // mbarriers of a CTA (map below)
   constexpr uint32_t OUT_SLOT_BYTES = 32 * 32;        // one 16-column group of a warp's 32 rows, dense bf16 (TMA store box)
   constexpr uint32_t OUT_SLOTS_PER_WARP = SDRM_OUT_SLOTS;
   static_assert(NSTG * STG_BYTES + 8 * NBAR + 256 + EPI_WARPS * (BIAS_SLICE_BYTES + OUT_SLOTS_PER_WARP * OUT_SLOT_BYTES) + 128 + 1023 <= ENGINE_SMEM_BYTES, "smem budget");
@@ -183,11 +183,14 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const uint32_t bar_half_read = bar_a_ready + 16u;
   // column-split mode: epilogue warps -> relay warp ("this CTA's chunk of the layer's output is in the L2"), a ring of two
   auto bar_relay = [&](uint32_t k) { return bar_a_ready + 24u + 8u * (k & 1u); };
+  // multi-resolution chains on a CTA pair: the peer's tile start step has arrived (one phase per tile iteration)
+  const uint32_t bar_pair_T = bar_a_ready + 40u;
   // per-role layer counters: two bits per sub-tile (k mod 4 is all the ring index and the parity need)
   auto cnt_get = [](uint32_t cnt, int s) -> uint32_t { return (cnt >> (2 * s)) & 3u; };
   auto cnt_inc = [](uint32_t cnt, int s) -> uint32_t { return (cnt & ~(3u << (2 * s))) | ((((cnt >> (2 * s)) + 1u) & 3u) << (2 * s)); };
   uint8_t* misc = smem + NSTG * STG_BYTES + 8 * NBAR;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc);       // 4 B
+  volatile int* peer_T = reinterpret_cast<volatile int*>(misc + 4);                // 1 int: the peer CTA's start step of the current tile (written by the peer)
   volatile int* tile_T = reinterpret_cast<volatile int*>(misc + 8);                // 2 ints
   volatile int* warp_max = reinterpret_cast<volatile int*>(misc + 16);             // 2 x EPI_WARPS ints
   uint8_t* bias_slices = smem + ((NSTG * STG_BYTES + 8 * NBAR + 16 + 8 * EPI_WARPS + 15) & ~15);   // EPI_WARPS x BIAS_SLICE_BYTES, 16-byte aligned
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
     mbar_init(bar_half_read, 1);
     mbar_init(bar_relay(0), EPI_WARPS);
     mbar_init(bar_relay(1), EPI_WARPS);
+    mbar_init(bar_pair_T, 1);
     fence_mbar_init();
   }
   if (warp == M_WARP) {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       const int ns = nsub_of(it);
       if (!PAIR && tile_of(it, 0) >= n_tiles) break;
       int T_tile = P.T;
-      if (!is_w || !PAIR) {   // (single mode: T_tile may be per tile)
+      if (!is_w || !PAIR || P.t_start != nullptr) {   // (single mode and multi-resolution pairs: T_tile is per tile / per pair)
         mbar_wait(bar_tile_ready, it & 1, err, WD_PRODUCER_TILE);
         T_tile = tile_T[it & 1];
       }
@@ -501,8 +505,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
       for (int it = 0; it < n_iters; ++it) {
         if (!PAIR && tile_of(it, 0) >= n_tiles) break;
         const int ns = nsub_of(it);
-        int T_tile = P.T;   // the pair mode only runs full-resolution chains (same T for both row tiles)
-        if (!PAIR) {
+        int T_tile = P.T;   // (multi-resolution pairs: both row tiles run the longer of their two chains, see the epilogue warps)
+        if (!PAIR || P.t_start != nullptr) {
           mbar_wait(bar_tile_ready, it & 1, err, WD_MMA_TILE);
           T_tile = tile_T[it & 1];
         }
@@ -861,6 +865,20 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
 #pragma unroll
       for (int w = 0; w < EPI_WARPS; ++w) T_tile = max(T_tile, warp_max[(it & 1) * EPI_WARPS + w]);
       if (P.n_step == 0) T_tile = 0;
+      if (PAIR && P.t_start != nullptr) {
+        // Multi-resolution chains on a CTA pair: the UMMAs of the two row tiles are one instruction stream, so both tiles run
+        // max(T_a, T_b) steps -- rows whose own chain is shorter stay inactive until their start step, exactly like the
+        // shorter rows inside one tile (the public call sorts the rows by chain length, so neighbouring tiles differ little).
+        // Once per tile: thread 0 drops its tile's start step into the peer's shared memory and arrives on the peer's barrier
+        // with a cluster-scope release; everybody acquires the own barrier and takes the maximum.
+        if (warp == 0 && lane == 0) {
+          const uint32_t peer = cta_rank ^ 1u;
+          asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_cluster(smem_u32(const_cast<int*>(peer_T)), peer)), "r"(T_tile) : "memory");
+          mbar_arrive_cluster_release(mapa_cluster(bar_pair_T, peer));
+        }
+        mbar_wait<true>(bar_pair_T, static_cast<uint32_t>(it) & 1u, err, WD_EPI_LAYER);
+        T_tile = max(T_tile, *peer_T);
+      }
 
       // ---- x_T and the first denoiser input (train_SDRM.py:51 / 38).  Once per tile: not performance critical.
       if (P.n_step > 0) {

@@ -95,17 +95,32 @@ def test_single_and_pair_mode_are_bit_identical():
     n, I, H, L, T, nh, nd = 1400, 700, 200, 264, 7, 2, 1.0     # 11 row tiles; ragged last tile; a ghost tile for the last pair
     diff, vae = random_modules(I, H, L, T, nh, seed=6, device="cuda")
     eng = _engine(diff, vae, T, nd)
-    outs = {}
+    outs, rnd, srt = {}, {}, {}
+    rng = np.random.RandomState(9)
+    t_any = torch.from_numpy(rng.randint(1, T, size=n).astype(np.int32)).cuda()      # multi-resolution chains, rows in any order
+    order = np.argsort(-t_any.cpu().numpy(), kind="stable").astype(np.int32)          # ... and sorted by chain length (the public call)
+    t_sorted, row_ids = t_any[torch.from_numpy(order).cuda().long()].contiguous(), torch.from_numpy(order).cuda()
     try:
         for c in (1, 2):
             eng.set_option(_lib.OPT_CLUSTER, c)
             outs[c] = eng.sample(n, seed=77, check=True).clone()
             assert lib.sdrm_last_cluster_size(eng.handle) == c
+            # a pair runs the longer of its two tiles' chains; rows with shorter chains wait for their start step
+            rnd[c] = eng.sample(n, t_start=t_any, seed=77, check=True).clone()
+            assert lib.sdrm_last_cluster_size(eng.handle) == c
+            srt[c] = eng.sample(n, t_start=t_sorted, row_ids=row_ids, seed=77, check=True).clone()
+            eng.set_option(_lib.OPT_GRID_LIMIT, 4)                                    # several tiles per CTA
+            assert torch.equal(eng.sample(n, t_start=t_sorted, row_ids=row_ids, seed=77, check=True), srt[c])
+            eng.set_option(_lib.OPT_GRID_LIMIT, 0)
     finally:
         eng.set_option(_lib.OPT_CLUSTER, 0)
+        eng.set_option(_lib.OPT_GRID_LIMIT, 0)
     assert lib.sdrm_resident_ctas(eng.handle, 2) >= 2 and lib.sdrm_resident_ctas(eng.handle, 4) == 0
     for c in outs:
         assert torch.equal(outs[1], outs[c]), c
+        assert torch.equal(rnd[1], rnd[c]) and torch.equal(srt[1], srt[c]), c
+    assert torch.equal(rnd[1], srt[1])      # a row's chain does not depend on where the row sits in the launch
+    assert not torch.equal(outs[1], rnd[1])
 
 
 @pytest.mark.parametrize("shape", [

@@ -22,7 +22,7 @@ K = "layer_engine_kernel.cuh"
 src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "sdrm_b200", "csrc", K)).read().splitlines()
 def line_of(marker):
     return next(i + 1 for i, l in enumerate(src) if marker in l)
-marks = [("producers", line_of("const bool is_w = (warp == W_WARP)")), ("mma", line_of("uint32_t stage = 0, sphase = 0, cc = 0;")),
+marks = [("producers", line_of("const bool is_w = (warp == W_WARP)")), ("mma", line_of("uint32_t stage = 0, sphase = 0, cc = 0")),
          ("epilogue", line_of("const int q = warp & 3;")), ("noise", line_of("const int full_groups = L >> 4;")),
          ("exit", line_of("nobody exits") - 3), ("end", len(src) + 1)]
 def first_addr(lo, hi):

@@ -14,7 +14,9 @@
 //   * warps 0-11 = epilogue, 12-15 = noise, 16 = weight TMA producer, 17 = UMMA issuer, 18 = activation TMA producer;
 //     the epilogue
 //     warps also pre-compute the Gaussian half of each step's posterior update while the tensor core is busy.
-// Rows are independent, so there is no inter-CTA synchronisation anywhere.
+// Rows are independent, so the streaming / resident flows need no synchronisation between row tiles (a tcgen05 pair shares its
+// barriers, and on multi-resolution launches its two tiles' start steps).  The column-split instantiation (SPLITK, below) is the
+// exception by design: a cluster of CTAs shares ONE row tile and hands the layer outputs around through cluster-wide chunk barriers.
 #pragma once
 #include "layer_engine.cuh"
 #include "philox.cuh"

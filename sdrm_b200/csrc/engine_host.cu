@@ -40,7 +40,8 @@ static Geom make_geom(int N, int K) {
 
 // Column-split geometry (clusters of SPLIT_S CTAs per row tile, see the kernel): a layer of fewer than SPLIT_S chunks is re-cut
 // into SPLIT_S narrower ones, so that every CTA of the cluster owns one -- half the weight bytes and half the epilogue per SM
-// of the 4-chunk geometry (the L2 -> SM port, ~64 B/clk, bounds a split layer: A image + own weight slices).
+// of a 4-chunk geometry.  (A UMMA costs ~60 ns whatever its N <= 208, so the narrower chunks do not shorten a layer's tensor
+// phase; they shorten everything around it: profiles/k1_split_r02.txt.)
 constexpr int SPLIT_S = 8;
 static Geom make_geom_split(int N, int K) {
   Geom g = make_geom(N, K);
@@ -232,7 +233,7 @@ struct sdrm_handle {
   float nd = 1.0f;
   Geom g0, gh, go;
   uint8_t *w0 = nullptr, *wh = nullptr, *wo = nullptr;
-  // column-split geometry (8 chunks per layer) and its weight images; packed for denoisers wider than 512 (>= 3 normal chunks)
+  // column-split geometry (8 chunks per layer) and its weight images; packed for every denoiser the tcgen05 engine takes (> 64 wide)
   Geom s0, sh, so, s1, s2;
   uint8_t *w0s = nullptr, *whs = nullptr, *wos = nullptr, *w1s = nullptr, *w2s = nullptr;
   bool split_den = false, split_dec = false;
@@ -705,10 +706,11 @@ int sdrm_sample(sdrm_handle* h, int64_t n, int64_t row_offset, const int32_t* d_
   };
   // chain layers ping-pong between activation buffers 0/1 (the kernel derives the parity); decoder descriptors name
   // their hi buffers RELATIVE to the chain's last output (0 = that buffer, 1 = the other), lo buffers are 2 and 3
-  // Column-split mode (see the kernel): full-resolution chains of a FEW row tiles of a WIDE denoiser (>= 3 N chunks per chain
-  // layer, i.e. wider than the resident flow takes): a cluster of S CTAs per tile, CTA j computes the chunks c = j (mod S).  One
-  // tile per cluster, all clusters resident at once.  Preferred: S = 8 in the 8-chunk geometry (second set of weight images);
-  // else S = 2 / 4 in the normal geometry (2 / 3 - 4 chunks).
+  // Column-split mode (see the kernel): launches of a FEW row tiles (the dataset-sized calls of the reference: the latency
+  // regime).  A cluster of S CTAs per tile, CTA j computes the chunks c = j (mod S); one tile per cluster, all clusters resident
+  // at once.  Preferred: S = 8 in the 8-chunk geometry (second set of weight images); when 8 CTAs per tile do not fit, the largest
+  // S = 4 / 2 that does, in the normal geometry (denoisers of >= 2 chunks).  Measured against the pair flows on every BASELINE
+  // configuration and on mid-size launches up to 74 tiles (profiles/k1_split_r02.txt): always faster.
   const long long n_tiles = (n + TILE_M - 1) / TILE_M;
   int split = 0;
   bool split_geom = false;

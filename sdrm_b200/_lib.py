@@ -29,6 +29,7 @@ SIGNATURES = {
     "sdrm_last_cluster_size": (C.c_int, [_P]),
     "sdrm_last_resident_mode": (C.c_int, [_P]),
     "sdrm_last_split_size": (C.c_int, [_P]),
+    "sdrm_layer_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "sdrm_resident_ctas": (C.c_int, [_P, C.c_int]),
     "sdrm_probe_linear": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "sdrm_topk": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int64, C.c_int, _P, _P, _P]),

@@ -933,6 +933,13 @@ int sdrm_set_option(sdrm_handle* h, int option, int64_t value) {
 int sdrm_resident_ctas(const sdrm_handle* h, int cluster) { return (h && cluster >= 1 && cluster <= 8) ? h->resident[cluster] : 0; }
 int sdrm_last_cluster_size(const sdrm_handle* h) { return h ? h->last_cluster : 0; }
 
+int sdrm_layer_geometry(int N, int K, int column_split, int* n_chunks, int* chunk_cols, int* k_blocks) {
+  if (N < 1 || K < 1 || !n_chunks || !chunk_cols || !k_blocks) return sdrm_fail(SDRM_ERR_BAD_ARG, "sdrm_layer_geometry: bad argument");
+  const Geom g = column_split ? make_geom_split(N, K) : make_geom(N, K);
+  *n_chunks = g.NCH; *chunk_cols = g.NC; *k_blocks = g.KB;
+  return SDRM_OK;
+}
+
 size_t sdrm_probe_linear_workspace_bytes(int64_t M, int K, int N) {
   if (M <= 0 || K <= 0 || N <= 0) return 0;
   Geom g; size_t act, w, b, s, total;

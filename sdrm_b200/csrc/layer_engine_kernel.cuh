@@ -50,6 +50,12 @@
                               // 0 = the epilogue warps arrive on the peers' chunk barriers themselves (default: 2.70 -> 2.54 ms at cfg 1 for dropping
                               // the release alone)
 #endif
+#ifndef SDRM_RES_CLUSTER_SCOPE
+#define SDRM_RES_CLUSTER_SCOPE 0   // resident flow: 1 = the peer's "tile written" signal is a cluster-scope release and the UMMA issuer fences at
+                                   // cluster scope behind its wait (~1.6 us per layer, see profiles/k1_split_r02.txt).  Not needed: the peer's half of
+                                   // the M = 256 operand is written by the peer's threads into the PEER's shared memory (fence.proxy.async there) and
+                                   // read by the peer SM's own tensor core; the leader's thread only orders its instruction issue behind the barrier.
+#endif
 #ifndef SDRM_STATE_CS
 #define SDRM_STATE_CS 1       // fp32 state accesses carry the streaming (.cs, evict-first) hint
 #endif
@@ -496,7 +502,11 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
         const int n_layers = n_iters * P.T * P.n_step;   // (both CTAs of a pair run the same number of tile iterations)
         for (int k = 0; k < n_layers; ++k) {
           mbar_wait(bar_a_ready, static_cast<uint32_t>(k) & 1u, err, WD_RELAY);
+#if SDRM_RES_CLUSTER_SCOPE
           if (elect_one()) mbar_arrive_cluster_release(remote);
+#else
+          if (elect_one()) mbar_arrive_cluster(remote);
+#endif
           __syncwarp();
         }
       }
@@ -522,7 +532,9 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
             mbar_wait(bar_a_ready, a_par, err, WD_MMA_AREADY);
             mbar_wait(bar_peer_ready, a_par, err, WD_MMA_PEER);
             a_par ^= 1u;
+#if SDRM_RES_CLUSTER_SCOPE
             fence_acq_rel_cluster();
+#endif
             tc_fence_after();
             SDRM_TR(1, 7);
           }

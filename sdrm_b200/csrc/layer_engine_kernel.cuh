@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   //                             act_chunk[MAX_SUB][MAX_ACT_CHUNKS] | state_ready[MAX_SUB] | noise_ready[MAX_SUB] |
   //                             layer_consumed[MAX_SUB][2] | discard_done[MAX_SUB][2]
   // column-split mode: the stage size follows the launch's widest chunk (A 16 KB + NC x 128 B of weights), so that up to 6 stages
-  // fit the same 192 KB ring -- a split layer is bound by the hops of the ring (commit -> empty -> producer -> full -> issuer),
-  // not by bytes: measured with the loads switched off it ran only 7 % faster
+  // fit the same 192 KB ring.  (Measured at cfg 1: 6 stages of 32 KB run like 4 of 48 KB -- neither the ring depth nor the bytes
+  // bound a split layer, its single-warp control loops did: profiles/k1_split_r02.txt.)
   constexpr int NSTG_B = SPLITK ? 6 : NSTG;   // barrier slots per array (2 x 6 fit the 3 x 4 slots of the single-CTA map)
   static_assert(2 * NSTG_B <= 3 * NSTG, "full / empty barrier slots");
   const uint32_t stg_bytes = SPLITK ? P.split_stage_bytes : STG_BYTES;
@@ -208,9 +208,10 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t leader_rank = cta_rank & ~1u;   // CTA of this tcgen05 pair that issues the UMMAs and owns the barriers
-  // Column-split mode (SPLIT): the latency regime of WIDE denoisers (a handful of row tiles, chain layers of 3 - 8 N chunks: the
-  // ml-100k configuration has 7 tiles of 830 columns).  One SM per tile spends a layer's whole N x K on ONE tensor core while 140 SMs
-  // idle, and the resident flow does not fit (tile > shared memory, N > 512 TMEM columns).  Here a cluster of S = 2 / 4 / 8 CTAs owns
+  // Column-split mode (SPLIT): the latency regime -- launches of a handful of row tiles, the reference's own dataset-sized calls
+  // (the ml-100k configuration has 7 tiles of 830 columns).  One SM per tile spends a layer's whole N x K on ONE tensor core while
+  // 140 SMs idle (and at 830 columns the resident flow does not fit: tile > shared memory, N > 512 TMEM columns).  Here a cluster
+  // of S = 2 / 4 / 8 CTAs owns
   // ONE row tile: CTA j computes the N chunks c = j (mod S) of every layer over the full K -- it streams the whole activation image
   // and only its own chunks' weights -- and owns the same columns of the fp32 state, the keep bits and the noise.  Activations
   // still travel through the tile's scratch in the L2 (TMA store -> TMA load), but the chunk barriers now span the cluster: once
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(ENGINE_THREADS, 1) sdrm_layer_engine_kernel(co
           while (ready < prev_nch && covered < lim) {
             covered += prev_nc;
             // (split mode: the chunk was written by another CTA's TMA stores, whose completion that CTA has observed (bulk wait_group)
-            // before its relay warp arrived here: the bytes are in the L2, and the only reader is this warp's TMA load, which reads
+            // before it arrived here: the bytes are in the L2, and the only reader is this warp's TMA load, which reads
             // the L2 directly -- no cache of this SM is involved.  A cluster-scope acquire costs ~1 us per wait, as a fence behind the
             // wait (fence.acq_rel.cluster) and as a qualifier on it (try_wait.acquire.cluster) alike: 8 of them were 60 % of a layer.)
 #ifdef SDRM_SPLIT_ACQUIRE_CLUSTER
